@@ -1,0 +1,235 @@
+// Fused self-attention for the MPNet encoder: softmax(q.k^T/sqrt(dh) + rel_bias + mask) . v
+// per (sequence, head), never materialising the [S,S] probability matrix in HBM.
+// Follows MPNetSelfAttention.forward (modeling_mpnet.py:162-177) with the shared relative
+// position bias of MPNetEncoder.compute_position_bias (:324-360) and the additive mask
+// (1-m)*finfo.min of get_extended_attention_mask (modeling_utils.py:936-947).
+//
+// One CTA per (sequence, head): K and V of the head ([S,64] bf16 each) are staged once in
+// shared memory (XOR-swizzled 16-byte chunks, conflict-free for ldmatrix); each warp then
+// runs a flash-style online softmax over 16-query-row blocks with bf16 mma.sync tiles and
+// fp32 statistics/accumulators.
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace arb {
+
+constexpr int kAttnThreads = 256;
+constexpr int kDH = 64;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kMaskMin = -3.4028234663852886e38f;  // torch.finfo(float32).min
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                            uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1,
+                                                  uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+template <bool kF16>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
+                                          uint32_t b1) {
+    if constexpr (kF16) {
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+            "{%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    } else {
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+            "{%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <bool kF16>
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias, int max_rel,
+                 const int32_t* __restrict__ mask, h16* __restrict__ ctx, int S, int heads,
+                 float scale_log2e) {
+    extern __shared__ __align__(128) uint8_t smem_attn[];
+    const int Spad = (S + 63) & ~63;
+    uint8_t* sK = smem_attn;                                  // [Spad][128 B], swizzled
+    uint8_t* sV = sK + static_cast<size_t>(Spad) * 128;       // [Spad][128 B], swizzled
+    float* sBias = reinterpret_cast<float*>(sV + static_cast<size_t>(Spad) * 128);  // [2S-1]
+    float* sMask = sBias + (2 * S - 1 + 3) / 4 * 4;           // [Spad] additive, log2 domain
+
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int H = heads * kDH;
+    const int64_t ld = 3 * static_cast<int64_t>(H);
+    const h16* base = qkv + static_cast<int64_t>(b) * S * ld;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- stage K, V (zero rows beyond S), bias slice and mask
+    const uint32_t sK_u = smem_u32(sK), sV_u = smem_u32(sV);
+    for (int idx = tid; idx < Spad * 16; idx += kAttnThreads) {
+        const int r = idx >> 4, c = idx & 7, isv = (idx >> 3) & 1;
+        const uint32_t dst = (isv ? sV_u : sK_u) + r * 128 + ((c ^ (r & 7)) << 4);
+        if (r < S) {
+            cp_async16(dst, base + static_cast<int64_t>(r) * ld + (isv ? 2 * H : H) + h * kDH + c * 8);
+        } else {
+            *reinterpret_cast<uint4*>((isv ? sV : sK) + r * 128 + ((c ^ (r & 7)) << 4)) =
+                make_uint4(0, 0, 0, 0);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int i = tid; i < 2 * S - 1; i += kAttnThreads) {
+        // entry i <-> relative position (j - i_q) = i - (S-1)
+        sBias[i] = rel_bias[static_cast<int64_t>(h) * (2 * max_rel - 1) + (i - (S - 1)) + (max_rel - 1)] * kLog2e;
+    }
+    for (int j = tid; j < Spad; j += kAttnThreads) {
+        float m = -INFINITY;  // keys beyond the sequence never contribute
+        if (j < S) m = mask[static_cast<int64_t>(b) * S + j] != 0 ? 0.f : kMaskMin;
+        sMask[j] = m;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    const int g = lane >> 2, t = lane & 3;
+    const int nqb = (S + 15) / 16;
+    for (int qb = warp; qb < nqb; qb += kAttnThreads / 32) {
+        const int q0 = qb * 16;
+        const int r0 = min(q0 + g, S - 1), r1 = min(q0 + g + 8, S - 1);
+        // Q fragments straight from global in the m16n8k16 A layout
+        uint32_t qa[4][4];
+        {
+            const h16* q_r0 = base + static_cast<int64_t>(r0) * ld + h * kDH;
+            const h16* q_r1 = base + static_cast<int64_t>(r1) * ld + h * kDH;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                qa[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(q_r0 + ks * 16 + 2 * t));
+                qa[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(q_r1 + ks * 16 + 2 * t));
+                qa[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(q_r0 + ks * 16 + 8 + 2 * t));
+                qa[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(q_r1 + ks * 16 + 8 + 2 * t));
+            }
+        }
+        float o[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+        const int i0 = q0 + g, i1 = q0 + g + 8;  // unclamped query indices for the bias lookup
+
+        for (int kb = 0; kb < Spad; kb += 64) {
+            float s[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+            // ---- S = Q.K^T
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                const int key = kb + nb * 8 + (lane & 7);
+#pragma unroll
+                for (int kp = 0; kp < 2; ++kp) {
+                    uint32_t b0, b1, b2, b3;
+                    const int chunk = 4 * kp + (lane >> 3);
+                    ldmatrix_x4(sK_u + key * 128 + ((chunk ^ (key & 7)) << 4), b0, b1, b2, b3);
+                    mma_16816<kF16>(s[nb], qa[2 * kp], b0, b1);
+                    mma_16816<kF16>(s[nb], qa[2 * kp + 1], b2, b3);
+                }
+            }
+            // ---- scale + relative-position bias + mask (log2 domain), block row max
+            float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                const int j = kb + nb * 8 + 2 * t;
+                const float mk0 = sMask[j], mk1 = sMask[j + 1];
+                // bias index (j - i) + (S-1); clamp only matters for rows/keys outside [0,S)
+                const int ba = min(max(j - i0 + S - 1, 0), 2 * S - 2);
+                const int bb = min(max(j - i1 + S - 1, 0), 2 * S - 2);
+                s[nb][0] = fmaf(s[nb][0], scale_log2e, sBias[ba]) + mk0;
+                s[nb][1] = fmaf(s[nb][1], scale_log2e, sBias[min(ba + 1, 2 * S - 2)]) + mk1;
+                s[nb][2] = fmaf(s[nb][2], scale_log2e, sBias[bb]) + mk0;
+                s[nb][3] = fmaf(s[nb][3], scale_log2e, sBias[min(bb + 1, 2 * S - 2)]) + mk1;
+                bm0 = fmaxf(bm0, fmaxf(s[nb][0], s[nb][1]));
+                bm1 = fmaxf(bm1, fmaxf(s[nb][2], s[nb][3]));
+            }
+            bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffff, bm0, 1));
+            bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffff, bm0, 2));
+            bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffff, bm1, 1));
+            bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffff, bm1, 2));
+            const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
+            const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+            m0 = mn0;
+            m1 = mn1;
+            float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                s[nb][0] = exp2f(s[nb][0] - mn0);
+                s[nb][1] = exp2f(s[nb][1] - mn0);
+                s[nb][2] = exp2f(s[nb][2] - mn1);
+                s[nb][3] = exp2f(s[nb][3] - mn1);
+                rs0 += s[nb][0] + s[nb][1];
+                rs1 += s[nb][2] + s[nb][3];
+            }
+            l0 = l0 * c0 + rs0;
+            l1 = l1 * c1 + rs1;
+#pragma unroll
+            for (int db = 0; db < 8; ++db) {
+                o[db][0] *= c0;
+                o[db][1] *= c0;
+                o[db][2] *= c1;
+                o[db][3] *= c1;
+            }
+            // ---- O += P.V
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                uint32_t pa[4];
+                pa[0] = pack16x2<kF16>(s[2 * kk][0], s[2 * kk][1]);
+                pa[1] = pack16x2<kF16>(s[2 * kk][2], s[2 * kk][3]);
+                pa[2] = pack16x2<kF16>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+                pa[3] = pack16x2<kF16>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+                const int key = kb + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+                for (int dp = 0; dp < 4; ++dp) {
+                    uint32_t b0, b1, b2, b3;
+                    const int chunk = 2 * dp + (lane >> 4);
+                    ldmatrix_x4_trans(sV_u + key * 128 + ((chunk ^ (key & 7)) << 4), b0, b1, b2, b3);
+                    mma_16816<kF16>(o[2 * dp], pa, b0, b1);
+                    mma_16816<kF16>(o[2 * dp + 1], pa, b2, b3);
+                }
+            }
+        }
+        // ---- finalise: row sums across the 4 lanes of a quad, normalise, store bf16
+        l0 += __shfl_xor_sync(0xffffffff, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffff, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffff, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffff, l1, 2);
+        const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+        h16* out0 = ctx + (static_cast<int64_t>(b) * S + i0) * H + h * kDH + 2 * t;
+        h16* out1 = ctx + (static_cast<int64_t>(b) * S + i1) * H + h * kDH + 2 * t;
+#pragma unroll
+        for (int db = 0; db < 8; ++db) {
+            if (i0 < S) *reinterpret_cast<uint32_t*>(out0 + db * 8) = pack16x2<kF16>(o[db][0] * inv0, o[db][1] * inv0);
+            if (i1 < S) *reinterpret_cast<uint32_t*>(out1 + db * 8) = pack16x2<kF16>(o[db][2] * inv1, o[db][3] * inv1);
+        }
+    }
+}
+
+int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
+                     h16* ctx, int B, int S, int heads, int dh, bool fp16, cudaStream_t stream) {
+    ARB_REQUIRE(qkv && rel_bias && mask && ctx, "attention: null pointer");
+    ARB_REQUIRE(dh == kDH, "attention: head dim %d unsupported (only 64)", dh);
+    ARB_REQUIRE(B > 0 && S > 0 && S <= 768 && S <= max_rel, "attention: bad shape B=%d S=%d max_rel=%d", B, S, max_rel);
+    ARB_REQUIRE(B <= 65535, "attention: batch %d exceeds grid.y", B);
+    const int Spad = (S + 63) & ~63;
+    const size_t smem = static_cast<size_t>(Spad) * 256 + ((2 * S - 1 + 3) / 4 * 4 + Spad) * sizeof(float);
+    auto kern = fp16 ? attention_kernel<true> : attention_kernel<false>;
+    ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    const float scale_log2e = kLog2e / sqrtf(static_cast<float>(dh));
+    kern<<<dim3(heads, B), kAttnThreads, smem, stream>>>(qkv, rel_bias, max_rel, mask, ctx, S, heads,
+                                                         scale_log2e);
+    ARB_CHECK_CUDA(cudaGetLastError());
+    return ARB_OK;
+}
+
+}  // namespace arb

@@ -1,0 +1,349 @@
+// extern "C" surface declared in include/arxiv_rag_b200.h: the MPNet encoder handle, the
+// search entry points and thin per-kernel wrappers. No torch types, no exceptions.
+#include <cuda_fp16.h>
+#include <math.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/arxiv_rag_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace arb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// ---- MPNetEncoder.relative_position_bucket (modeling_mpnet.py:343-360), float32 like torch.
+static int relative_bucket(int relative_position, int num_buckets, int max_distance) {
+    int n = -relative_position;
+    const int nb = num_buckets / 2;
+    int ret = 0;
+    if (n < 0) {
+        ret += nb;
+        n = -n;
+    }
+    const int max_exact = nb / 2;
+    if (n < max_exact) return ret + n;
+    const float a = logf(static_cast<float>(n) / static_cast<float>(max_exact));
+    const float b = a / static_cast<float>(log(static_cast<double>(max_distance) / max_exact));
+    const float c = b * static_cast<float>(nb - max_exact);
+    int v = max_exact + static_cast<int>(c);
+    if (v > nb - 1) v = nb - 1;
+    return ret + v;
+}
+
+struct LayerDev {
+    h16 *w_qkv, *w_o, *w_in, *w_out;  // [3H,H] [H,H] [I,H] [H,I]
+    float *b_qkv, *b_o, *b_in, *b_out;
+    float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+
+struct Mpnet {
+    ArbMpnetConfig cfg;
+    int device = 0;
+    int64_t max_tokens = 0;
+    int max_seq = 0;
+    int64_t bytes = 0;
+    std::vector<void*> allocs;
+    float *word_emb = nullptr, *pos_emb = nullptr, *emb_g = nullptr, *emb_b = nullptr;
+    float* rel_bias = nullptr;  // [heads, 2*max_seq-1], entry r <-> j-i = r-(max_seq-1)
+    std::vector<LayerDev> layers;
+    h16 *h = nullptr, *h1 = nullptr, *tmp = nullptr, *ctx = nullptr, *qkv = nullptr, *ffn = nullptr;
+    bool fp16 = false;
+
+    template <typename T>
+    int alloc(T** p, size_t count) {
+        void* d = nullptr;
+        ARB_CHECK_CUDA(cudaMalloc(&d, count * sizeof(T)));
+        allocs.push_back(d);
+        bytes += static_cast<int64_t>(count * sizeof(T));
+        *p = static_cast<T*>(d);
+        return ARB_OK;
+    }
+    int upload_f32(float** dst, const float* src, size_t count) {
+        ARB_REQUIRE(src != nullptr, "mpnet_create: missing weight array");
+        if (int rc = alloc(dst, count)) return rc;
+        ARB_CHECK_CUDA(cudaMemcpy(*dst, src, count * sizeof(float), cudaMemcpyHostToDevice));
+        return ARB_OK;
+    }
+    // fp32 host values -> 16-bit (round-to-nearest-even) device
+    int upload16(h16* dst, const float* src, size_t count) {
+        ARB_REQUIRE(src != nullptr, "mpnet_create: missing weight matrix");
+        std::vector<h16> tmpv(count);
+        if (fp16) {
+            for (size_t i = 0; i < count; ++i) tmpv[i] = __half_as_ushort(__float2half_rn(src[i]));
+        } else {
+            for (size_t i = 0; i < count; ++i) tmpv[i] = __bfloat16_as_ushort(__float2bfloat16_rn(src[i]));
+        }
+        ARB_CHECK_CUDA(cudaMemcpy(dst, tmpv.data(), count * sizeof(h16), cudaMemcpyHostToDevice));
+        return ARB_OK;
+    }
+    ~Mpnet() {
+        for (void* p : allocs) cudaFree(p);
+    }
+};
+
+static int mpnet_build(Mpnet* m, const ArbMpnetWeights* w) {
+    const ArbMpnetConfig& c = m->cfg;
+    const size_t H = c.hidden_size, I = c.intermediate_size;
+    if (int rc = m->upload_f32(&m->word_emb, w->word_embeddings, static_cast<size_t>(c.vocab_size) * H)) return rc;
+    if (int rc = m->upload_f32(&m->pos_emb, w->position_embeddings, static_cast<size_t>(c.max_position_embeddings) * H)) return rc;
+    if (int rc = m->upload_f32(&m->emb_g, w->emb_ln_g, H)) return rc;
+    if (int rc = m->upload_f32(&m->emb_b, w->emb_ln_b, H)) return rc;
+    // expand the bucketed relative bias once: it depends only on j-i (modeling_mpnet.py:324-341)
+    {
+        ARB_REQUIRE(w->relative_attention_bias != nullptr, "mpnet_create: missing relative_attention_bias");
+        const int P = m->max_seq, W = 2 * P - 1;
+        std::vector<float> tbl(static_cast<size_t>(c.num_heads) * W);
+        for (int r = 0; r < W; ++r) {
+            const int bucket = relative_bucket(r - (P - 1), c.relative_attention_num_buckets, 128);
+            for (int hd = 0; hd < c.num_heads; ++hd)
+                tbl[static_cast<size_t>(hd) * W + r] = w->relative_attention_bias[static_cast<size_t>(bucket) * c.num_heads + hd];
+        }
+        if (int rc = m->upload_f32(&m->rel_bias, tbl.data(), tbl.size())) return rc;
+    }
+    m->layers.resize(c.num_layers);
+    for (int l = 0; l < c.num_layers; ++l) {
+        const ArbMpnetLayerWeights& lw = w->layers[l];
+        LayerDev& d = m->layers[l];
+        if (int rc = m->alloc(&d.w_qkv, 3 * H * H)) return rc;
+        if (int rc = m->upload16(d.w_qkv, lw.q_w, H * H)) return rc;
+        if (int rc = m->upload16(d.w_qkv + H * H, lw.k_w, H * H)) return rc;
+        if (int rc = m->upload16(d.w_qkv + 2 * H * H, lw.v_w, H * H)) return rc;
+        if (int rc = m->alloc(&d.b_qkv, 3 * H)) return rc;
+        ARB_REQUIRE(lw.q_b && lw.k_b && lw.v_b, "mpnet_create: missing q/k/v bias (layer %d)", l);
+        ARB_CHECK_CUDA(cudaMemcpy(d.b_qkv, lw.q_b, H * 4, cudaMemcpyHostToDevice));
+        ARB_CHECK_CUDA(cudaMemcpy(d.b_qkv + H, lw.k_b, H * 4, cudaMemcpyHostToDevice));
+        ARB_CHECK_CUDA(cudaMemcpy(d.b_qkv + 2 * H, lw.v_b, H * 4, cudaMemcpyHostToDevice));
+        if (int rc = m->alloc(&d.w_o, H * H)) return rc;
+        if (int rc = m->upload16(d.w_o, lw.o_w, H * H)) return rc;
+        if (int rc = m->upload_f32(&d.b_o, lw.o_b, H)) return rc;
+        if (int rc = m->upload_f32(&d.ln1_g, lw.attn_ln_g, H)) return rc;
+        if (int rc = m->upload_f32(&d.ln1_b, lw.attn_ln_b, H)) return rc;
+        if (int rc = m->alloc(&d.w_in, I * H)) return rc;
+        if (int rc = m->upload16(d.w_in, lw.ffn_in_w, I * H)) return rc;
+        if (int rc = m->upload_f32(&d.b_in, lw.ffn_in_b, I)) return rc;
+        if (int rc = m->alloc(&d.w_out, H * I)) return rc;
+        if (int rc = m->upload16(d.w_out, lw.ffn_out_w, H * I)) return rc;
+        if (int rc = m->upload_f32(&d.b_out, lw.ffn_out_b, H)) return rc;
+        if (int rc = m->upload_f32(&d.ln2_g, lw.out_ln_g, H)) return rc;
+        if (int rc = m->upload_f32(&d.ln2_b, lw.out_ln_b, H)) return rc;
+    }
+    const size_t T = static_cast<size_t>(m->max_tokens);
+    if (int rc = m->alloc(&m->h, T * H)) return rc;
+    if (int rc = m->alloc(&m->h1, T * H)) return rc;
+    if (int rc = m->alloc(&m->tmp, T * H)) return rc;
+    if (int rc = m->alloc(&m->ctx, T * H)) return rc;
+    if (int rc = m->alloc(&m->qkv, T * 3 * H)) return rc;
+    if (int rc = m->alloc(&m->ffn, T * I)) return rc;
+    return ARB_OK;
+}
+
+static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B, int S, float* out,
+                        cudaStream_t st) {
+    const ArbMpnetConfig& c = m->cfg;
+    const int H = c.hidden_size, I = c.intermediate_size;
+    const int64_t T = static_cast<int64_t>(B) * S;
+    int rc;
+    if ((rc = launch_embed_ln(ids, m->word_emb, m->pos_emb, m->emb_g, m->emb_b, m->h, B, S, H,
+                              c.vocab_size, c.max_position_embeddings, c.pad_token_id,
+                              c.layer_norm_eps, m->fp16, st)))
+        return rc;
+    for (int l = 0; l < c.num_layers; ++l) {
+        const LayerDev& d = m->layers[l];
+        // q,k,v projections as one [T,H] x [3H,H]^T GEMM (modeling_mpnet.py:145-159)
+        if ((rc = launch_gemm16(m->h, H, d.w_qkv, H, m->qkv, 3 * H, d.b_qkv, nullptr, 0, T, 3 * H, H, EPI_BIAS, m->fp16, st))) return rc;
+        // softmax(qk^T/8 + position_bias + mask) v (:162-177)
+        if ((rc = launch_attention(m->qkv, m->rel_bias, m->max_seq, mask, m->ctx, B, S, c.num_heads, H / c.num_heads, m->fp16, st))) return rc;
+        // o-projection + residual, then post-LN (:183, :210)
+        if ((rc = launch_gemm16(m->ctx, H, d.w_o, H, m->tmp, H, d.b_o, m->h, H, T, H, H, EPI_BIAS_RESIDUAL, m->fp16, st))) return rc;
+        if ((rc = launch_layernorm(m->tmp, d.ln1_g, d.ln1_b, m->h1, T, H, c.layer_norm_eps, m->fp16, st))) return rc;
+        // FFN: GELU(erf) fused in the up-projection epilogue (:225-228), residual in the down (:239-243)
+        if ((rc = launch_gemm16(m->h1, H, d.w_in, H, m->ffn, I, d.b_in, nullptr, 0, T, I, H, EPI_BIAS_GELU, m->fp16, st))) return rc;
+        if ((rc = launch_gemm16(m->ffn, I, d.w_out, I, m->tmp, H, d.b_out, m->h1, H, T, H, I, EPI_BIAS_RESIDUAL, m->fp16, st))) return rc;
+        if ((rc = launch_layernorm(m->tmp, d.ln2_g, d.ln2_b, m->h, T, H, c.layer_norm_eps, m->fp16, st))) return rc;
+    }
+    return launch_pool_normalize(m->h, mask, out, B, S, H, m->fp16, st);
+}
+
+}  // namespace arb
+
+using namespace arb;
+
+extern "C" {
+
+const char* arb_last_error(void) { return get_error(); }
+int arb_abi_version(void) { return 1; }
+
+int arb_mpnet_relative_bucket(int32_t relative_position, int32_t num_buckets, int32_t max_distance) {
+    return relative_bucket(relative_position, num_buckets, max_distance);
+}
+
+int arb_mpnet_create(const ArbMpnetConfig* cfg, const ArbMpnetWeights* weights, int64_t max_tokens,
+                     int32_t max_seq, int32_t device, void** handle) {
+    ARB_REQUIRE(cfg && weights && handle, "mpnet_create: null argument");
+    ARB_REQUIRE(weights->layers != nullptr, "mpnet_create: null layer array");
+    ARB_REQUIRE(cfg->hidden_size > 0 && cfg->num_heads > 0 && cfg->hidden_size % cfg->num_heads == 0,
+                "mpnet_create: bad hidden/heads %d/%d", cfg->hidden_size, cfg->num_heads);
+    ARB_REQUIRE(cfg->hidden_size / cfg->num_heads == 64, "mpnet_create: head dim %d unsupported (64 only)",
+                cfg->hidden_size / cfg->num_heads);
+    ARB_REQUIRE(cfg->hidden_size % 128 == 0 && cfg->hidden_size <= 1024, "mpnet_create: hidden size %d unsupported", cfg->hidden_size);
+    ARB_REQUIRE(cfg->intermediate_size % 32 == 0, "mpnet_create: intermediate size %d unsupported", cfg->intermediate_size);
+    ARB_REQUIRE(cfg->compute_dtype == ARB_DTYPE_BF16 || cfg->compute_dtype == ARB_DTYPE_F16,
+                "mpnet_create: compute_dtype %d must be ARB_DTYPE_BF16 or ARB_DTYPE_F16", cfg->compute_dtype);
+    ARB_REQUIRE(cfg->num_layers > 0 && cfg->vocab_size > 0 && cfg->max_position_embeddings > 2,
+                "mpnet_create: bad layer/vocab/position counts");
+    ARB_REQUIRE(max_tokens > 0 && max_seq > 0 && max_seq <= 768, "mpnet_create: bad max_tokens=%lld / max_seq=%d",
+                (long long)max_tokens, max_seq);
+    ARB_REQUIRE(max_seq + cfg->pad_token_id < cfg->max_position_embeddings,
+                "mpnet_create: max_seq %d exceeds the position table (%d rows)", max_seq, cfg->max_position_embeddings);
+    int ndev = 0;
+    ARB_CHECK_CUDA(cudaGetDeviceCount(&ndev));
+    ARB_REQUIRE(device >= 0 && device < ndev, "mpnet_create: no CUDA device %d (found %d) — this library has no CPU path", device, ndev);
+    ARB_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    ARB_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("mpnet_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return ARB_ERR_UNSUPPORTED;
+    }
+    Mpnet* m = new (std::nothrow) Mpnet();
+    ARB_REQUIRE(m != nullptr, "mpnet_create: out of host memory");
+    m->cfg = *cfg;
+    m->fp16 = cfg->compute_dtype == ARB_DTYPE_F16;
+    m->device = device;
+    m->max_tokens = max_tokens;
+    m->max_seq = max_seq;
+    int rc = mpnet_build(m, weights);
+    if (rc) {
+        delete m;
+        return rc;
+    }
+    ARB_CHECK_CUDA(cudaDeviceSynchronize());
+    *handle = m;
+    return ARB_OK;
+}
+
+int arb_mpnet_destroy(void* handle) {
+    if (handle) delete static_cast<Mpnet*>(handle);
+    return ARB_OK;
+}
+
+int64_t arb_mpnet_device_bytes(void* handle) { return handle ? static_cast<Mpnet*>(handle)->bytes : 0; }
+
+int arb_mpnet_launches_per_encode(void* handle) {
+    if (!handle) return 0;
+    return 2 + 7 * static_cast<Mpnet*>(handle)->cfg.num_layers;
+}
+
+int arb_mpnet_encode(void* handle, const int32_t* ids_dev, const int32_t* mask_dev, int32_t B,
+                     int32_t S, float* out_dev, void* stream) {
+    ARB_REQUIRE(handle && ids_dev && mask_dev && out_dev, "mpnet_encode: null argument");
+    Mpnet* m = static_cast<Mpnet*>(handle);
+    ARB_REQUIRE(B > 0 && S > 0, "mpnet_encode: empty batch B=%d S=%d", B, S);
+    ARB_REQUIRE(S <= m->max_seq, "mpnet_encode: S=%d exceeds max_seq=%d", S, m->max_seq);
+    ARB_REQUIRE(static_cast<int64_t>(B) * S <= m->max_tokens, "mpnet_encode: B*S=%lld exceeds max_tokens=%lld",
+                (long long)B * S, (long long)m->max_tokens);
+    return mpnet_encode(m, ids_dev, mask_dev, B, S, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+size_t arb_topk_search_workspace_bytes(int32_t dtype, int64_t Q, int64_t N, int32_t D, int32_t k) {
+    if (dtype == ARB_DTYPE_BF16) return search_workspace_bytes(Q, N, D, k);
+    if (dtype == ARB_DTYPE_F32) return search_f32_workspace_bytes(Q, N, D, k);
+    return 0;
+}
+
+int arb_topk_search(const void* queries_dev, const void* corpus_dev, int32_t dtype, int64_t Q,
+                    int64_t N, int32_t D, int32_t k, float* out_scores_dev, int64_t* out_ids_dev,
+                    int64_t id_offset, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == ARB_DTYPE_BF16)
+        return launch_search_bf16(static_cast<const __nv_bfloat16*>(queries_dev),
+                                  static_cast<const __nv_bfloat16*>(corpus_dev), Q, N, D, k,
+                                  out_scores_dev, out_ids_dev, id_offset, workspace_dev, workspace_bytes, st);
+    if (dtype == ARB_DTYPE_F32)
+        return launch_search_f32(static_cast<const float*>(queries_dev), static_cast<const float*>(corpus_dev),
+                                 Q, N, D, k, out_scores_dev, out_ids_dev, id_offset, workspace_dev,
+                                 workspace_bytes, st);
+    set_error("topk_search: unknown dtype %d", dtype);
+    return ARB_ERR_INVALID;
+}
+
+int arb_topk_search_launches(int32_t dtype) { return dtype == ARB_DTYPE_F32 ? 5 : 2; }
+
+int arb_topk_merge(const float* scores_dev, const int64_t* ids_dev, int32_t G, int64_t Q, int32_t k,
+                   float* out_scores_dev, int64_t* out_ids_dev, void* stream) {
+    return launch_topk_merge(scores_dev, ids_dev, G, Q, k, out_scores_dev, out_ids_dev,
+                             static_cast<cudaStream_t>(stream));
+}
+
+static int dtype16(int32_t dtype, bool* fp16) {
+    ARB_REQUIRE(dtype == ARB_DTYPE_BF16 || dtype == ARB_DTYPE_F16, "dtype %d must be ARB_DTYPE_BF16 or ARB_DTYPE_F16", dtype);
+    *fp16 = dtype == ARB_DTYPE_F16;
+    return ARB_OK;
+}
+
+int arb_gemm16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+               const float* bias, const void* R, int64_t ldr, int64_t M, int32_t N, int32_t K,
+               int32_t epilogue, int32_t dtype, void* stream) {
+    bool f;
+    if (int rc = dtype16(dtype, &f)) return rc;
+    return launch_gemm16(static_cast<const h16*>(A), lda, static_cast<const h16*>(B), ldb, static_cast<h16*>(C),
+                         ldc, bias, static_cast<const h16*>(R), ldr, M, N, K, epilogue, f,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int arb_gemm16_f32out(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                      int64_t M, int32_t N, int32_t K, int32_t dtype, void* stream) {
+    bool f;
+    if (int rc = dtype16(dtype, &f)) return rc;
+    return launch_gemm16_f32out(static_cast<const h16*>(A), lda, static_cast<const h16*>(B), ldb, C, ldc, M, N,
+                                K, f, static_cast<cudaStream_t>(stream));
+}
+
+int arb_embed_layernorm(const int32_t* ids, const float* word_emb, const float* pos_emb,
+                        const float* gamma, const float* beta, void* out16, int32_t B, int32_t S,
+                        int32_t H, int32_t vocab, int32_t max_pos, int32_t pad_id, float eps,
+                        int32_t dtype, void* stream) {
+    bool f;
+    if (int rc = dtype16(dtype, &f)) return rc;
+    return launch_embed_ln(ids, word_emb, pos_emb, gamma, beta, static_cast<h16*>(out16), B, S, H, vocab,
+                           max_pos, pad_id, eps, f, static_cast<cudaStream_t>(stream));
+}
+
+int arb_layernorm16(const void* x, const float* gamma, const float* beta, void* out, int64_t rows,
+                    int32_t H, float eps, int32_t dtype, void* stream) {
+    bool f;
+    if (int rc = dtype16(dtype, &f)) return rc;
+    return launch_layernorm(static_cast<const h16*>(x), gamma, beta, static_cast<h16*>(out), rows, H, eps, f,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int arb_attention16(const void* qkv, const float* rel_bias, int32_t max_rel, const int32_t* mask,
+                    void* ctx, int32_t B, int32_t S, int32_t heads, int32_t head_dim, int32_t dtype,
+                    void* stream) {
+    bool f;
+    if (int rc = dtype16(dtype, &f)) return rc;
+    return launch_attention(static_cast<const h16*>(qkv), rel_bias, max_rel, mask, static_cast<h16*>(ctx), B, S,
+                            heads, head_dim, f, static_cast<cudaStream_t>(stream));
+}
+
+int arb_pool_normalize(const void* hidden16, const int32_t* mask, float* out, int32_t B, int32_t S,
+                       int32_t H, int32_t dtype, void* stream) {
+    bool f;
+    if (int rc = dtype16(dtype, &f)) return rc;
+    return launch_pool_normalize(static_cast<const h16*>(hidden16), mask, out, B, S, H, f,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,56 @@
+// Internal (C++) launch interface between the kernels and the C-ABI layer in capi.cu.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace arb {
+
+// Encoder activations/weights are 16-bit in HBM: bf16 or fp16, chosen per handle (`fp16` flag).
+typedef uint16_t h16;
+
+enum GemmEpilogue : int {
+    EPI_BIAS = 0,           // C = A.B^T + bias
+    EPI_BIAS_GELU = 1,      // C = gelu_erf(A.B^T + bias)
+    EPI_BIAS_RESIDUAL = 2,  // C = A.B^T + bias + R
+};
+
+// C[M,N] = epi(A[M,K] . B[N,K]^T); A, B, C, R 16-bit row-major; bias fp32 [N] (may be null).
+int launch_gemm16(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
+                  const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
+                  int epilogue, bool fp16, cudaStream_t stream);
+// Same main loop, fp32 output, no epilogue math (used by the kernel parity tests).
+int launch_gemm16_f32out(const h16* A, int64_t lda, const h16* B, int64_t ldb, float* C,
+                         int64_t ldc, int64_t M, int N, int K, bool fp16, cudaStream_t stream);
+
+// word_emb[ids] + pos_emb[position_ids(ids)] -> LayerNorm -> 16-bit hidden [B*S, H]
+int launch_embed_ln(const int32_t* ids, const float* word_emb, const float* pos_emb,
+                    const float* gamma, const float* beta, h16* out, int B, int S, int H, int vocab,
+                    int max_pos, int pad_id, float eps, bool fp16, cudaStream_t stream);
+// out = LayerNorm(x) row-wise, x 16-bit [rows, H] (already holds GEMM output + residual).
+int launch_layernorm(const h16* x, const float* gamma, const float* beta, h16* out, int64_t rows,
+                     int H, float eps, bool fp16, cudaStream_t stream);
+// masked mean over tokens then L2 normalise: hidden [B,S,H], mask int32 [B,S] -> fp32 [B,H]
+int launch_pool_normalize(const h16* hidden, const int32_t* mask, float* out, int B, int S, int H,
+                          bool fp16, cudaStream_t stream);
+// softmax(q.k^T/sqrt(dh) + rel_bias[h][j-i] + mask) . v for every (batch, head);
+// qkv [B*S, 3*H] (q | k | v column blocks), rel_bias fp32 [heads, 2*max_rel-1]
+// (entry r <-> j-i = r-(max_rel-1)), mask int32 [B,S]; ctx [B*S, H].
+int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
+                     h16* ctx, int B, int S, int heads, int dh, bool fp16, cudaStream_t stream);
+
+// Search: fused score GEMM + per-query running top-k over a bf16 corpus.
+size_t search_workspace_bytes(int64_t Q, int64_t N, int D, int k);
+int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int64_t Q, int64_t N,
+                       int D, int k, float* out_scores, int64_t* out_ids, int64_t id_offset,
+                       void* workspace, size_t ws_bytes, cudaStream_t stream);
+// fp32 operands: bf16 hi/lo split scoring + exact fp32 re-score of the candidates.
+size_t search_f32_workspace_bytes(int64_t Q, int64_t N, int D, int k);
+int launch_search_f32(const float* q, const float* corpus, int64_t Q, int64_t N, int D, int k,
+                      float* out_scores, int64_t* out_ids, int64_t id_offset, void* workspace,
+                      size_t ws_bytes, cudaStream_t stream);
+// k-way merge of G per-shard top-k lists: [G,Q,k] -> [Q,k], order (score desc, id asc).
+int launch_topk_merge(const float* scores, const int64_t* ids, int G, int64_t Q, int k,
+                      float* out_scores, int64_t* out_ids, cudaStream_t stream);
+
+}  // namespace arb

@@ -1,0 +1,459 @@
+// Exact cosine top-k search: scores = Q . C^T on tcgen05 tensor cores with the per-query
+// running top-k fused into the TMEM epilogue, so the [Q, N] score matrix never reaches HBM.
+// The reference has no search routine; the semantic definition generalised here is
+// TextChunker._cosine_similarity (3-chunks/pipeline/src/processors/text_processor.py:1601-1605)
+// on unit-norm rows (generate_embeddings_parallel.py:149 normalize_embeddings=True), with
+// top_k from 3-chunks/pipeline/config.yaml:62-64. Ties are ordered by ascending row id.
+//
+// Work decomposition: item = (corpus split, 128-query tile), split-major, dealt round-robin to a
+// persistent grid so the CTAs running together sweep the same corpus region (L2 reuse). Each
+// epilogue thread owns one query row (one TMEM lane): it scans the 256 scores of every chunk
+// against its current k-th best and inserts the rare survivors into a sorted list in shared
+// memory. Per-item lists go to the workspace and a k-way merge kernel produces the final order.
+#include "common.cuh"
+#include "kernels.h"
+#include "tmap.cuh"
+#include "umma_pipe.cuh"
+
+namespace arb {
+
+constexpr int kSBN = 256;     // corpus rows per chunk (MMA N)
+constexpr int kMaxK = 128;    // sorted lists: 128 rows x k x 8 B of shared memory
+// smem ring depth: 3 x 48 KB stages when the lists need <= 64 KB (k <= 64), else 2 stages
+
+struct SearchPlan {
+    int nq;        // 128-query tiles
+    int nchunks;   // corpus chunks of kSBN rows
+    int nsplit;    // corpus splits
+    int cps;       // chunks per split (last split may be short)
+    int grid;
+};
+
+static SearchPlan make_plan(int64_t Q, int64_t N) {
+    SearchPlan p;
+    p.nq = static_cast<int>((Q + kBM - 1) / kBM);
+    p.nchunks = static_cast<int>((N + kSBN - 1) / kSBN);
+    const int G = num_sms();
+    // Pick the split count that wastes the fewest CTA-rounds; prefer fewer splits on ties
+    // (less merge work). Keep at least 4 chunks per split when the corpus allows it.
+    int best = 1;
+    double best_eff = -1.0;
+    const int max_split = p.nchunks < 4 ? 1 : (p.nchunks / 4 < 4 * G ? p.nchunks / 4 : 4 * G);
+    for (int s = 1; s <= max_split; ++s) {
+        const int cps = (p.nchunks + s - 1) / s;
+        const int s_eff = (p.nchunks + cps - 1) / cps;  // splits actually non-empty
+        if (s_eff != s) continue;
+        const int64_t items = static_cast<int64_t>(p.nq) * s;
+        const int64_t rounds = (items + G - 1) / G;
+        // time ~ rounds * cps ; ideal ~ nq * nchunks / G
+        const double eff = (static_cast<double>(p.nq) * p.nchunks / G) / (static_cast<double>(rounds) * cps);
+        if (eff > best_eff + 0.02) {
+            best_eff = eff;
+            best = s;
+        }
+        if (items >= 16ll * G && eff > 0.97) break;
+    }
+    p.nsplit = best;
+    p.cps = (p.nchunks + best - 1) / best;
+    const int64_t items = static_cast<int64_t>(p.nq) * p.nsplit;
+    p.grid = static_cast<int>(items < G ? items : G);
+    return p;
+}
+
+// Yields the (query-tile row, corpus chunk row) sequence of this CTA's items.
+struct SearchTileIter {
+    int item, step, items, nq, cps, nchunks;
+    int chunk = 0, chunk_end = 0, row_q = 0;
+    __device__ __forceinline__ SearchTileIter(int first, int step_, int items_, int nq_, int cps_,
+                                              int nchunks_)
+        : item(first), step(step_), items(items_), nq(nq_), cps(cps_), nchunks(nchunks_) {}
+    __device__ __forceinline__ bool next(int& row_a, int& row_b) {
+        while (chunk >= chunk_end) {
+            if (item >= items) return false;
+            const int split = item / nq;
+            row_q = (item % nq) * kBM;
+            chunk = split * cps;
+            chunk_end = min(chunk + cps, nchunks);
+            item += step;
+        }
+        row_a = row_q;
+        row_b = chunk * kSBN;
+        ++chunk;
+        return true;
+    }
+};
+
+// Sorted insert into this thread's list (column `row` of the [k][128] arrays). Strict '<' keeps
+// earlier (smaller-id) entries ahead of equal scores: ids arrive in increasing order.
+__device__ __forceinline__ float list_insert(float* ls, int* li, int k, float v, int id) {
+    int i = k - 1;
+    while (i > 0 && ls[(i - 1) * kBM] < v) {
+        ls[i * kBM] = ls[(i - 1) * kBM];
+        li[i * kBM] = li[(i - 1) * kBM];
+        --i;
+    }
+    ls[i * kBM] = v;
+    li[i * kBM] = id;
+    return ls[(k - 1) * kBM];
+}
+
+template <int kSStages>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                   const __grid_constant__ CUtensorMap tmap_c, float* __restrict__ part_scores,
+                   int32_t* __restrict__ part_ids, int64_t Q, int64_t N, int D, int k, int nq, int cps,
+                   int nchunks, int nsplit) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    PipeSmem<kSBN, kSStages> sm{smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)};
+    const int warp = __shfl_sync(0xffffffff, threadIdx.x / 32, 0);
+    const int lane = threadIdx.x & 31;
+    const int kblocks = (D + kBK - 1) / kBK;
+    const int items = nq * nsplit;
+    SearchTileIter it(static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), items, nq, cps, nchunks);
+
+    const uint32_t tmem_base = pipe_setup(sm, warp, &tmap_q, &tmap_c);
+
+    if (warp == 0) {
+        // queries are re-read by every chunk -> keep in L2; the corpus streams through once per split
+        if (elect_one()) pipe_produce(sm, &tmap_q, &tmap_c, it, kblocks, kEvictLast, kEvictNormal);
+    } else if (warp == 1) {
+        if (elect_one()) pipe_mma<kSBN, kSStages, false>(sm, tmem_base, it, kblocks);
+    } else {
+        const int lane_grp = warp & 3;
+        const int trow = lane_grp * 32 + lane;  // row of the 128-query tile owned by this thread
+        float* ls = reinterpret_cast<float*>(sm.extra()) + trow;                 // [k][128]
+        int* li = reinterpret_cast<int*>(sm.extra() + static_cast<size_t>(k) * kBM * 4) + trow;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int split = item / nq;
+            const int qt = item % nq;
+            const int c_begin = split * cps;
+            const int c_end = min(c_begin + cps, nchunks);
+            for (int i = 0; i < k; ++i) {
+                ls[i * kBM] = -INFINITY;
+                li[i * kBM] = -1;
+            }
+            float thr = -INFINITY;
+            for (int chunk = c_begin; chunk < c_end; ++chunk) {
+                mbar_wait(sm.tmem_full(acc), acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
+                                       static_cast<uint32_t>(acc * kSBN);
+                const int64_t n0 = static_cast<int64_t>(chunk) * kSBN;
+                const int nvalid = static_cast<int>(N - n0 < kSBN ? N - n0 : kSBN);
+#pragma unroll 1
+                for (int c0 = 0; c0 < kSBN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + c0, r);
+                    tmem_ld_wait();
+                    if (c0 + 32 <= nvalid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = __uint_as_float(r[j]);
+                            if (v > thr) thr = list_insert(ls, li, k, v, static_cast<int>(n0) + c0 + j);
+                        }
+                    } else if (c0 < nvalid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = __uint_as_float(r[j]);
+                            if (c0 + j < nvalid && v > thr)
+                                thr = list_insert(ls, li, k, v, static_cast<int>(n0) + c0 + j);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(sm.tmem_empty(acc));
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+            // publish this item's list: part[split][query][k]
+            const int64_t qrow = static_cast<int64_t>(qt) * kBM + trow;
+            if (qrow < Q) {
+                float* ps = part_scores + (static_cast<int64_t>(split) * Q + qrow) * k;
+                int32_t* pi = part_ids + (static_cast<int64_t>(split) * Q + qrow) * k;
+                for (int i = 0; i < k; ++i) {
+                    ps[i] = ls[i * kBM];
+                    pi[i] = li[i * kBM];
+                }
+            }
+        }
+    }
+    pipe_teardown(sm, warp, tmem_base);
+}
+
+// ----------------------------------------------------------------------------- k-way merge
+// One warp per query. Every input list is sorted by (score desc, id asc); lane l owns lists
+// l, l+32, ... and offers the best of their heads each round; a warp arg-max picks the winner.
+template <typename IdT>
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(const float* __restrict__ scores, const IdT* __restrict__ ids, int G, int64_t Q,
+                  int k, int64_t id_offset, float* __restrict__ out_scores,
+                  int64_t* __restrict__ out_ids) {
+    extern __shared__ int s_pos_all[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* pos = s_pos_all + warp * G;
+    const int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
+    if (q >= Q) return;
+    for (int g = lane; g < G; g += 32) pos[g] = 0;
+    __syncwarp();
+    for (int r = 0; r < k; ++r) {
+        float bs = -INFINITY;
+        int64_t bi = INT64_MAX;
+        int bg = -1;
+        for (int g = lane; g < G; g += 32) {
+            const int p = pos[g];
+            if (p < k) {
+                const int64_t off = (static_cast<int64_t>(g) * Q + q) * k + p;
+                const float s = scores[off];
+                const int64_t id = static_cast<int64_t>(ids[off]);
+                if (id >= 0 && (bg < 0 || s > bs || (s == bs && id < bi))) {
+                    bs = s;
+                    bi = id;
+                    bg = g;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffff, bs, o);
+            const int64_t oi = __shfl_xor_sync(0xffffffff, bi, o);
+            const int og = __shfl_xor_sync(0xffffffff, bg, o);
+            if (og >= 0 && (bg < 0 || os > bs || (os == bs && oi < bi))) {
+                bs = os;
+                bi = oi;
+                bg = og;
+            }
+        }
+        if (lane == 0) {
+            out_scores[q * k + r] = bg >= 0 ? bs : -INFINITY;
+            out_ids[q * k + r] = bg >= 0 ? bi + id_offset : -1;
+        }
+        if (bg >= 0 && (bg & 31) == lane) pos[bg] += 1;
+        __syncwarp();
+    }
+}
+
+template <typename IdT>
+static int launch_merge_impl(const float* scores, const IdT* ids, int G, int64_t Q, int k,
+                             int64_t id_offset, float* out_scores, int64_t* out_ids,
+                             cudaStream_t stream) {
+    const int warps = 8;
+    const size_t smem = static_cast<size_t>(warps) * G * sizeof(int);
+    ARB_REQUIRE(smem <= 48 * 1024, "topk_merge: too many lists (G=%d)", G);
+    const int64_t blocks = (Q + warps - 1) / warps;
+    ARB_REQUIRE(blocks < (1ll << 31), "topk_merge: Q too large");
+    topk_merge_kernel<IdT><<<static_cast<int>(blocks), warps * 32, smem, stream>>>(
+        scores, ids, G, Q, k, id_offset, out_scores, out_ids);
+    ARB_CHECK_CUDA(cudaGetLastError());
+    return ARB_OK;
+}
+
+int launch_topk_merge(const float* scores, const int64_t* ids, int G, int64_t Q, int k,
+                      float* out_scores, int64_t* out_ids, cudaStream_t stream) {
+    ARB_REQUIRE(scores && ids && out_scores && out_ids, "topk_merge: null pointer");
+    ARB_REQUIRE(G > 0 && Q > 0 && k > 0, "topk_merge: bad shape G=%d Q=%lld k=%d", G, (long long)Q, k);
+    return launch_merge_impl<int64_t>(scores, ids, G, Q, k, 0, out_scores, out_ids, stream);
+}
+
+// ----------------------------------------------------------------------------- bf16 search
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+size_t search_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
+    (void)D;
+    if (Q <= 0 || N <= 0 || k <= 0) return 0;
+    const SearchPlan p = make_plan(Q, N);
+    const size_t per = static_cast<size_t>(p.nsplit) * Q * k;
+    return align_up(per * 4, 256) + align_up(per * 4, 256);
+}
+
+int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int64_t Q, int64_t N,
+                       int D, int k, float* out_scores, int64_t* out_ids, int64_t id_offset,
+                       void* workspace, size_t ws_bytes, cudaStream_t stream) {
+    ARB_REQUIRE(q && corpus && out_scores && out_ids, "search: null pointer");
+    ARB_REQUIRE(Q > 0 && N > 0, "search: empty problem Q=%lld N=%lld", (long long)Q, (long long)N);
+    ARB_REQUIRE(D > 0 && D % 8 == 0, "search: D=%d must be a positive multiple of 8", D);
+    ARB_REQUIRE(k > 0 && k <= kMaxK, "search: k=%d out of range [1,%d]", k, kMaxK);
+    ARB_REQUIRE(N < (1ll << 31) - kSBN, "search: shard too large (N=%lld); shard the corpus", (long long)N);
+    ARB_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(corpus) & 15) == 0,
+                "search: operands must be 16-byte aligned");
+    const size_t need = search_workspace_bytes(Q, N, D, k);
+    if (workspace == nullptr || ws_bytes < need) {
+        set_error("search: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+        return ARB_ERR_WORKSPACE;
+    }
+    const SearchPlan p = make_plan(Q, N);
+    const size_t per = static_cast<size_t>(p.nsplit) * Q * k;
+    float* part_scores = reinterpret_cast<float*>(workspace);
+    int32_t* part_ids = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) + align_up(per * 4, 256));
+
+    CUtensorMap tq, tc;
+    if (!make_tmap_bf16_k64(&tq, q, static_cast<uint64_t>(Q), static_cast<uint64_t>(D), static_cast<uint64_t>(D), kBM) ||
+        !make_tmap_bf16_k64(&tc, corpus, static_cast<uint64_t>(N), static_cast<uint64_t>(D), static_cast<uint64_t>(D), kSBN)) {
+        set_error("search: cuTensorMapEncodeTiled failed");
+        return ARB_ERR_CUDA;
+    }
+    if (k <= 64) {
+        const int smem = PipeSmem<kSBN, 3>::kExtraOffset + k * kBM * 8 + 1024;
+        ARB_CHECK_CUDA(cudaFuncSetAttribute(search_topk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        search_topk_kernel<3><<<p.grid, kPipeThreads, smem, stream>>>(
+            tq, tc, part_scores, part_ids, Q, N, D, k, p.nq, p.cps, p.nchunks, p.nsplit);
+    } else {
+        const int smem = PipeSmem<kSBN, 2>::kExtraOffset + k * kBM * 8 + 1024;
+        ARB_CHECK_CUDA(cudaFuncSetAttribute(search_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        search_topk_kernel<2><<<p.grid, kPipeThreads, smem, stream>>>(
+            tq, tc, part_scores, part_ids, Q, N, D, k, p.nq, p.cps, p.nchunks, p.nsplit);
+    }
+    ARB_CHECK_CUDA(cudaGetLastError());
+    return launch_merge_impl<int32_t>(part_scores, part_ids, p.nsplit, Q, k, id_offset, out_scores,
+                                      out_ids, stream);
+}
+
+// ----------------------------------------------------------------------------- fp32 search
+// fp32 operands are scored on the bf16 tensor cores through a hi/lo split folded into K:
+//   x = hi + lo (both bf16, |x - hi - lo| <= 2^-17 |x|),
+//   q.c ~= q_hi.c_hi + q_lo.c_hi + q_hi.c_lo = [q_hi | q_lo | q_hi] . [c_hi | c_hi | c_lo]
+// i.e. one bf16 search with D' = 3D (error ~4e-7 on unit vectors of dim 768, well inside the
+// 1e-5 tie tolerance). The k + kF32Margin survivors are then re-scored with exact fp32 FMAs and
+// re-ranked, so the returned scores are true fp32 dot products.
+constexpr int kF32Margin = 8;
+
+template <bool kIsQuery>
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t rows, int D) {
+    const int64_t total = rows * (D / 4);
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = i / (D / 4);
+        const int c = static_cast<int>(i % (D / 4)) * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * D + c));
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            hi[j] = __float2bfloat16_rn(f[j]);
+            lo[j] = __float2bfloat16_rn(f[j] - __bfloat162float(hi[j]));
+        }
+        __nv_bfloat16* o = out + r * 3 * D + c;
+        uint2 uh, ul;
+        uh.x = (uint32_t)__bfloat16_as_ushort(hi[0]) | ((uint32_t)__bfloat16_as_ushort(hi[1]) << 16);
+        uh.y = (uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(hi[3]) << 16);
+        ul.x = (uint32_t)__bfloat16_as_ushort(lo[0]) | ((uint32_t)__bfloat16_as_ushort(lo[1]) << 16);
+        ul.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16);
+        *reinterpret_cast<uint2*>(o) = uh;
+        *reinterpret_cast<uint2*>(o + D) = kIsQuery ? ul : uh;
+        *reinterpret_cast<uint2*>(o + 2 * D) = kIsQuery ? uh : ul;
+    }
+}
+
+// One warp per query: exact fp32 dot for each candidate, then rank by (score desc, id asc).
+__global__ void __launch_bounds__(128)
+rescore_f32_kernel(const float* __restrict__ q, const float* __restrict__ corpus, int64_t Q, int D,
+                   int kc, int k, const int64_t* __restrict__ cand_ids, int64_t id_offset,
+                   float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+    extern __shared__ uint8_t smem_rs[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    float* sc = reinterpret_cast<float*>(smem_rs) + warp * kc;
+    int64_t* si = reinterpret_cast<int64_t*>(smem_rs + static_cast<size_t>(nw) * kc * 4 +
+                                             (static_cast<size_t>(nw) * kc * 4) % 8) + warp * kc;
+    const int64_t qi = static_cast<int64_t>(blockIdx.x) * nw + warp;
+    if (qi >= Q) return;
+    const float* qr = q + qi * D;
+    for (int c = 0; c < kc; ++c) {
+        const int64_t id = cand_ids[qi * kc + c];  // already offset by id_offset
+        float acc = 0.f;
+        if (id >= 0) {
+            const float* cr = corpus + (id - id_offset) * D;
+            for (int d = lane * 4; d < D; d += 128) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(qr + d));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(cr + d));
+                acc = fmaf(a.x, b.x, acc);
+                acc = fmaf(a.y, b.y, acc);
+                acc = fmaf(a.z, b.z, acc);
+                acc = fmaf(a.w, b.w, acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffff, acc, o);
+        }
+        if (lane == 0) {
+            sc[c] = id >= 0 ? acc : -INFINITY;
+            si[c] = id;
+        }
+    }
+    __syncwarp();
+    for (int c = lane; c < kc; c += 32) {
+        const float s = sc[c];
+        const int64_t id = si[c];
+        int rank = 0;
+        for (int j = 0; j < kc; ++j) {
+            const float sj = sc[j];
+            const int64_t ij = si[j];
+            // candidates that sort strictly ahead of c; empty slots (id < 0) sort last
+            const bool ahead = (ij >= 0 && id < 0) || ((ij >= 0) == (id >= 0) && (sj > s || (sj == s && (ij < id || (ij == id && j < c)))));
+            rank += ahead ? 1 : 0;
+        }
+        if (rank < k) {
+            out_scores[qi * k + rank] = s;
+            out_ids[qi * k + rank] = id;
+        }
+    }
+}
+
+static void f32_layout(int64_t Q, int64_t N, int D, int k, size_t* off_q, size_t* off_c, size_t* off_cs,
+                       size_t* off_ci, size_t* off_inner, size_t* total) {
+    const int kc = k + kF32Margin < kMaxK ? k + kF32Margin : kMaxK;
+    size_t o = 0;
+    *off_q = o;  o += align_up(static_cast<size_t>(Q) * 3 * D * 2, 256);
+    *off_c = o;  o += align_up(static_cast<size_t>(N) * 3 * D * 2, 256);
+    *off_cs = o; o += align_up(static_cast<size_t>(Q) * kc * 4, 256);
+    *off_ci = o; o += align_up(static_cast<size_t>(Q) * kc * 8, 256);
+    *off_inner = o; o += search_workspace_bytes(Q, N, 3 * D, kc);
+    *total = o;
+}
+
+size_t search_f32_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
+    if (Q <= 0 || N <= 0 || k <= 0 || D <= 0) return 0;
+    size_t a, b, c, d, e, t;
+    f32_layout(Q, N, D, k, &a, &b, &c, &d, &e, &t);
+    return t;
+}
+
+int launch_search_f32(const float* q, const float* corpus, int64_t Q, int64_t N, int D, int k,
+                      float* out_scores, int64_t* out_ids, int64_t id_offset, void* workspace,
+                      size_t ws_bytes, cudaStream_t stream) {
+    ARB_REQUIRE(q && corpus && out_scores && out_ids, "search_f32: null pointer");
+    ARB_REQUIRE(Q > 0 && N > 0, "search_f32: empty problem Q=%lld N=%lld", (long long)Q, (long long)N);
+    ARB_REQUIRE(D > 0 && D % 8 == 0, "search_f32: D=%d must be a positive multiple of 8", D);
+    ARB_REQUIRE(k > 0 && k <= kMaxK, "search_f32: k=%d out of range [1,%d]", k, kMaxK);
+    ARB_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(corpus) & 15) == 0,
+                "search_f32: operands must be 16-byte aligned");
+    size_t off_q, off_c, off_cs, off_ci, off_inner, total;
+    f32_layout(Q, N, D, k, &off_q, &off_c, &off_cs, &off_ci, &off_inner, &total);
+    if (workspace == nullptr || ws_bytes < total) {
+        set_error("search_f32: workspace too small (%zu < %zu bytes)", ws_bytes, total);
+        return ARB_ERR_WORKSPACE;
+    }
+    const int kc = k + kF32Margin < kMaxK ? k + kF32Margin : kMaxK;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    __nv_bfloat16* q3 = reinterpret_cast<__nv_bfloat16*>(ws + off_q);
+    __nv_bfloat16* c3 = reinterpret_cast<__nv_bfloat16*>(ws + off_c);
+    float* cs = reinterpret_cast<float*>(ws + off_cs);
+    int64_t* ci = reinterpret_cast<int64_t*>(ws + off_ci);
+    const int blocks = num_sms() * 8;
+    split_bf16_kernel<true><<<blocks, 256, 0, stream>>>(q, q3, Q, D);
+    split_bf16_kernel<false><<<blocks, 256, 0, stream>>>(corpus, c3, N, D);
+    ARB_CHECK_CUDA(cudaGetLastError());
+    int rc = launch_search_bf16(q3, c3, Q, N, 3 * D, kc, cs, ci, id_offset, ws + off_inner,
+                                ws_bytes - off_inner, stream);
+    if (rc) return rc;
+    const int nw = 4;
+    const size_t smem = static_cast<size_t>(nw) * kc * 4 + 8 + static_cast<size_t>(nw) * kc * 8;
+    rescore_f32_kernel<<<static_cast<int>((Q + nw - 1) / nw), nw * 32, smem, stream>>>(
+        q, corpus, Q, D, kc, k, ci, id_offset, out_scores, out_ids);
+    ARB_CHECK_CUDA(cudaGetLastError());
+    return ARB_OK;
+}
+
+}  // namespace arb

@@ -1,0 +1,159 @@
+// Warp-specialised TMA -> smem ring -> tcgen05.mma -> TMEM pipeline shared by the encoder
+// GEMMs and the search score kernel. One CTA per SM, 6 warps:
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      TMEM owner + MMA issuer (one elected lane)
+//   warps 2..5  epilogue: TMEM -> registers -> (bias/GELU/residual store | running top-k)
+// Tiles are 128 (M) x BN (N) x 64 (K-block); A and B are both K-major bf16, loaded with the
+// 128-byte swizzle. The fp32 accumulator is double buffered in TMEM (2 x BN columns) so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+#pragma once
+#include "ptx.cuh"
+
+namespace arb {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kPipeThreads = 192;
+
+template <int BN, int STAGES>
+struct PipeSmem {
+    static constexpr int kABytes = kBM * kBK * 2;
+    static constexpr int kBBytes = BN * kBK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = STAGES * kStageBytes;
+    // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] + tmem base ptr
+    static constexpr int kBarBytes = (2 * STAGES + 4) * 8 + 16;
+    static constexpr int kExtraOffset = kBarOffset + ((kBarBytes + 127) / 128) * 128;
+
+    uint8_t* base;
+    __device__ __forceinline__ uint8_t* a(int s) const { return base + s * kStageBytes; }
+    __device__ __forceinline__ uint8_t* b(int s) const { return base + s * kStageBytes + kABytes; }
+    __device__ __forceinline__ uint64_t* full(int s) const {
+        return reinterpret_cast<uint64_t*>(base + kBarOffset) + s;
+    }
+    __device__ __forceinline__ uint64_t* empty(int s) const {
+        return reinterpret_cast<uint64_t*>(base + kBarOffset) + STAGES + s;
+    }
+    __device__ __forceinline__ uint64_t* tmem_full(int s) const {
+        return reinterpret_cast<uint64_t*>(base + kBarOffset) + 2 * STAGES + s;
+    }
+    __device__ __forceinline__ uint64_t* tmem_empty(int s) const {
+        return reinterpret_cast<uint64_t*>(base + kBarOffset) + 2 * STAGES + 2 + s;
+    }
+    __device__ __forceinline__ uint32_t* tmem_ptr() const {
+        return reinterpret_cast<uint32_t*>(base + kBarOffset + (2 * STAGES + 4) * 8);
+    }
+    __device__ __forceinline__ uint8_t* extra() const { return base + kExtraOffset; }
+};
+
+// Barrier init + TMEM allocation; returns the TMEM base address to every thread.
+template <int BN, int STAGES>
+__device__ __forceinline__ uint32_t pipe_setup(const PipeSmem<BN, STAGES>& sm, int warp,
+                                               const void* tmap_a, const void* tmap_b) {
+    constexpr uint32_t kTmemCols = (2 * BN <= 32)    ? 32
+                                   : (2 * BN <= 64)  ? 64
+                                   : (2 * BN <= 128) ? 128
+                                   : (2 * BN <= 256) ? 256
+                                                     : 512;
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(tmap_a);
+        tma_prefetch_desc(tmap_b);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(sm.full(s), 1);
+            mbar_init(sm.empty(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(sm.tmem_full(s), 1);
+            mbar_init(sm.tmem_empty(s), 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(sm.tmem_ptr(), kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return *sm.tmem_ptr();
+}
+
+template <int BN, int STAGES>
+__device__ __forceinline__ void pipe_teardown(const PipeSmem<BN, STAGES>& sm, int warp,
+                                              uint32_t tmem_base) {
+    constexpr uint32_t kTmemCols = (2 * BN <= 32)    ? 32
+                                   : (2 * BN <= 64)  ? 64
+                                   : (2 * BN <= 128) ? 128
+                                   : (2 * BN <= 256) ? 256
+                                                     : 512;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// Producer: for every tile the iterator yields, stream its K-blocks through the ring.
+// TileIter: bool next(int& row_a, int& row_b) — first rows of the A and B tiles.
+template <int BN, int STAGES, class TileIter>
+__device__ __forceinline__ void pipe_produce(const PipeSmem<BN, STAGES>& sm, const void* tmap_a,
+                                             const void* tmap_b, TileIter it, int kblocks,
+                                             uint64_t hint_a, uint64_t hint_b) {
+    int stage = 0;
+    uint32_t phase = 0;
+    int row_a, row_b;
+    while (it.next(row_a, row_b)) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(sm.empty(stage), phase ^ 1);
+            mbar_arrive_expect_tx(sm.full(stage), PipeSmem<BN, STAGES>::kStageBytes);
+            tma_load_2d(tmap_a, sm.full(stage), sm.a(stage), kb * kBK, row_a, hint_a);
+            tma_load_2d(tmap_b, sm.full(stage), sm.b(stage), kb * kBK, row_b, hint_b);
+            if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+    }
+}
+
+// MMA issuer: 4 x (128 x BN x 16) tcgen05.mma per K-block, accumulating in the TMEM buffer
+// that the epilogue has released; commits release the smem stage and publish the accumulator.
+template <int BN, int STAGES, bool kF16, class TileIter>
+__device__ __forceinline__ void pipe_mma(const PipeSmem<BN, STAGES>& sm, uint32_t tmem_base,
+                                         TileIter it, int kblocks) {
+    constexpr uint32_t idesc = umma_idesc_16bit(kBM, BN, kF16);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int row_a, row_b;
+    while (it.next(row_a, row_b)) {
+        mbar_wait(sm.tmem_empty(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(sm.full(stage), phase);
+            tc_fence_after();
+            const uint64_t da = umma_desc_sw128(smem_u32(sm.a(stage)));
+            const uint64_t db = umma_desc_sw128(smem_u32(sm.b(stage)));
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+                // +32 bytes per K=16 step inside the 128-byte swizzle atom -> +2 in addr>>4 units
+                umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(sm.empty(stage));
+            if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+        umma_commit(sm.tmem_full(acc));
+        if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+        }
+    }
+}
+
+}  // namespace arb

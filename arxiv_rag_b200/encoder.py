@@ -1,0 +1,190 @@
+"""B200SentenceEncoder — drop-in for the `SentenceTransformer('all-mpnet-base-v2')` object that
+`generate_embeddings_parallel.py` keeps in `_worker_model` (:37, :47) and calls as
+`model.encode(batch, batch_size=..., normalize_embeddings=True, show_progress_bar=False,
+convert_to_numpy=True, convert_to_tensor=False)` (:146-153, :160-165) and
+`model.get_sentence_embedding_dimension()` (:169).
+
+Semantics restated from sentence-transformers `encode`: sort inputs by length
+descending, batch, pad each batch to its longest row, MPNet forward, masked mean-pool,
+L2-normalise, undo the sort, return float32 `[n, 768]` rows in input order.
+
+All arithmetic runs in the CUDA library (`_lib`); torch is used for device memory, pinned
+staging buffers and streams only. There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _lib
+from .weights import ALL_MPNET_BASE_V2, MPNetArch, PackedWeights, synthetic_state_dict
+
+
+def _require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("arxiv_rag_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+    return torch
+
+
+class B200SentenceEncoder:
+    """MPNet sentence encoder resident on one B200.
+
+    Parameters
+    ----------
+    state_dict : HF `MPNetModel.state_dict()` (or numpy arrays under the same names).  None ->
+        seeded synthetic weights (`weights.synthetic_state_dict(seed)`), since no checkpoint
+        exists offline.
+    tokenizer : optional callable `tokenizer(list[str], padding=True, truncation=True,
+        max_length=..., return_tensors='np') -> {'input_ids', 'attention_mask'}` (a HF tokenizer).
+        Without one, `encode` accepts pre-tokenised `(input_ids, attention_mask)`.
+    max_batch / max_seq : capacity of the activation workspace (tokens = max_batch * max_seq).
+    dtype : 'bf16' (the BASELINE config) or 'fp16' — the 16-bit format of weights/activations and
+        tensor-core operands (fp32 accumulation and statistics either way). fp16's 3 extra
+        mantissa bits give cosine ~0.999998 vs fp32 on every row; bf16 gives ~0.99995 on full
+        rows but drops below 0.9999 on very short rows (DESIGN.md 'Numerics').
+    """
+
+    def __init__(self, state_dict: dict | None = None, arch: MPNetArch = ALL_MPNET_BASE_V2,
+                 device: int | None = None, max_batch: int = 1024, max_seq: int | None = None,
+                 tokenizer=None, seed: int = 0, dtype: str = "bf16"):
+        torch = _require_cuda()
+        self._torch = torch
+        self.arch = arch
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.max_seq = int(max_seq or arch.max_seq_length)
+        self.max_batch = int(max_batch)
+        self.tokenizer = tokenizer
+        self.max_seq_length = min(arch.max_seq_length, self.max_seq)
+        if state_dict is None:
+            state_dict = synthetic_state_dict(arch, seed)
+        packed = PackedWeights(arch, state_dict)
+        if dtype not in ("bf16", "fp16"):
+            raise ValueError("dtype must be 'bf16' (BASELINE config) or 'fp16'")
+        self.dtype = dtype
+        cfg = arch.c_struct(_lib.ARB_DTYPE_F16 if dtype == "fp16" else _lib.ARB_DTYPE_BF16)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().arb_mpnet_create(C.byref(cfg), C.byref(packed.struct),
+                                                   self.max_batch * self.max_seq, self.max_seq,
+                                                   self.device, C.byref(handle)))
+        self._h = handle
+        self._staging = {}
+
+    # ------------------------------------------------------------------ reference surface
+    def get_sentence_embedding_dimension(self) -> int:
+        return self.arch.hidden_size
+
+    def encode(self, sentences, batch_size: int = 32, show_progress_bar: bool | None = None,
+               convert_to_numpy: bool = True, convert_to_tensor: bool = False,
+               normalize_embeddings: bool = False, **_ignored):
+        """Same call shape as SentenceTransformer.encode. all-mpnet-base-v2 ends with a Normalize
+        module, so rows are unit-norm whether or not `normalize_embeddings` is set."""
+        torch = self._torch
+        single = isinstance(sentences, str)
+        ids, mask = self._tokenize([sentences] if single else sentences)
+        n = ids.shape[0]
+        out = torch.empty((n, self.arch.hidden_size), dtype=torch.float32, device=f"cuda:{self.device}")
+        if n:
+            lengths = mask.sum(axis=1)
+            order = np.argsort(-lengths, kind="stable")  # longest first, like sentence-transformers
+            bs = max(1, min(int(batch_size), self.max_batch))
+            with torch.cuda.device(self.device):
+                for start in range(0, n, bs):
+                    sel = order[start:start + bs]
+                    S = max(int(lengths[sel].max()), 1)  # pad to the longest row of the batch
+                    d_ids, d_mask = self._to_device(ids[sel, :S], mask[sel, :S])
+                    emb = self.encode_tokens(d_ids, d_mask)
+                    out[torch.from_numpy(sel).to(out.device)] = emb
+        if convert_to_tensor:
+            return out[0] if single else out
+        res = out.cpu().numpy()
+        return res[0] if single else res
+
+    # ------------------------------------------------------------------ device fast path
+    def encode_tokens(self, ids_dev, mask_dev, out=None):
+        """ids/mask: CUDA int32 [B,S] tensors -> CUDA float32 [B,H] (enqueued on the current stream)."""
+        torch = self._torch
+        if ids_dev.dtype != torch.int32 or mask_dev.dtype != torch.int32:
+            raise TypeError("encode_tokens expects int32 CUDA tensors")
+        if not (ids_dev.is_cuda and mask_dev.is_cuda and ids_dev.is_contiguous() and mask_dev.is_contiguous()):
+            raise ValueError("encode_tokens expects contiguous CUDA tensors")
+        B, S = ids_dev.shape
+        if out is None:
+            out = torch.empty((B, self.arch.hidden_size), dtype=torch.float32, device=ids_dev.device)
+        _lib.check(_lib.lib().arb_mpnet_encode(self._h, _lib.ptr(ids_dev), _lib.ptr(mask_dev), B, S,
+                                               _lib.ptr(out), _lib.current_stream()))
+        return out
+
+    @property
+    def launches_per_encode(self) -> int:
+        return int(_lib.lib().arb_mpnet_launches_per_encode(self._h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(_lib.lib().arb_mpnet_device_bytes(self._h))
+
+    # ------------------------------------------------------------------ helpers
+    def _tokenize(self, sentences) -> tuple[np.ndarray, np.ndarray]:
+        if isinstance(sentences, dict):
+            sentences = (sentences["input_ids"], sentences["attention_mask"])
+        if isinstance(sentences, tuple) and len(sentences) == 2 and not isinstance(sentences[0], str):
+            ids = np.asarray(_to_numpy(sentences[0]))
+            mask = np.asarray(_to_numpy(sentences[1]))
+        else:
+            sentences = list(sentences)
+            if len(sentences) == 0:
+                return (np.zeros((0, 1), np.int32), np.zeros((0, 1), np.int32))
+            if not isinstance(sentences[0], str):
+                raise TypeError("encode expects list[str] or a (input_ids, attention_mask) pair")
+            if self.tokenizer is None:
+                raise RuntimeError(
+                    "no tokenizer: the all-mpnet-base-v2 vocabulary is not available offline; pass "
+                    "tokenizer=... or pre-tokenised (input_ids, attention_mask)")
+            enc = self.tokenizer(sentences, padding=True, truncation=True,
+                                 max_length=self.max_seq_length, return_tensors="np")
+            ids, mask = np.asarray(enc["input_ids"]), np.asarray(enc["attention_mask"])
+        if ids.ndim != 2 or ids.shape != mask.shape:
+            raise ValueError(f"input_ids {ids.shape} / attention_mask {mask.shape} must be equal 2-D shapes")
+        if ids.shape[1] > self.max_seq:
+            ids, mask = ids[:, :self.max_seq], mask[:, :self.max_seq]  # tokenizer-style truncation
+        return ids.astype(np.int32, copy=False), mask.astype(np.int32, copy=False)
+
+    def _to_device(self, ids: np.ndarray, mask: np.ndarray):
+        """Pinned staging + async H2D on the current stream."""
+        torch = self._torch
+        B, S = ids.shape
+        key = (B, S)
+        if key not in self._staging:
+            if len(self._staging) > 64:
+                torch.cuda.synchronize(self.device)
+                self._staging.clear()
+            self._staging[key] = (torch.empty((2, B, S), dtype=torch.int32, pin_memory=True),
+                                  torch.cuda.Event())
+        st, ev = self._staging[key]
+        ev.synchronize()  # the previous H2D out of this pinned buffer must have drained
+        st[0].numpy()[...] = ids
+        st[1].numpy()[...] = mask
+        dev = st.to(f"cuda:{self.device}", non_blocking=True)
+        ev.record()
+        return dev[0], dev[1]
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().arb_mpnet_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _to_numpy(x):
+    if hasattr(x, "detach"):
+        return x.detach().cpu().numpy()
+    return x

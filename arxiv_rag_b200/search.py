@@ -1,0 +1,160 @@
+"""Exact cosine top-k search over a (row-sharded) chunk-embedding matrix.
+
+The reference implies but never wrote this stage (`retrieval.top_k: 10` at
+3-chunks/pipeline/config.yaml:62-64 is never read); its only cosine is
+`TextChunker._cosine_similarity` (text_processor.py:1601-1605). On the unit-norm rows that
+`encode(..., normalize_embeddings=True)` (generate_embeddings_parallel.py:149) produces, cosine
+is the dot product, so search is `top_k(Q @ C.T)` with ties ordered by ascending row id.
+
+Multi-GPU (one process per GPU, torch.distributed): the corpus is row-sharded, every rank runs
+the fused score+top-k kernel on its shard, the per-rank `[Q,k]` lists are all-gathered over
+NCCL/NVLink and merged by the k-way merge kernel (`arb_topk_merge`).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("arxiv_rag_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+    return torch
+
+
+def shard_bounds(n_rows: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous row range of `rank` (rows r*N/G .. (r+1)*N/G)."""
+    lo = (n_rows * rank) // world_size
+    hi = (n_rows * (rank + 1)) // world_size
+    return lo, hi
+
+
+class CorpusIndex:
+    """A corpus shard resident in HBM plus the reusable search workspace.
+
+    corpus : `[N, D]` float32 or bfloat16 (numpy / torch, host or device). float32 stays float32
+        (scored with the split-bf16 + fp32 re-score path); bf16 is searched as stored.
+    id_offset : global id of local row 0 (for row-sharded corpora).
+    """
+
+    def __init__(self, corpus, id_offset: int = 0, device: int | None = None, dtype=None):
+        torch = _torch()
+        self._torch = torch
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        dev = f"cuda:{self.device}"
+        if isinstance(corpus, np.ndarray):
+            corpus = torch.from_numpy(np.ascontiguousarray(corpus))
+        if dtype is not None:
+            corpus = corpus.to(dtype)
+        if corpus.dtype == torch.float64:  # the reference's embeddings.npy is float64 (:281-284)
+            corpus = corpus.to(torch.float32)
+        if corpus.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"corpus dtype {corpus.dtype} unsupported (float32 / bfloat16)")
+        if corpus.dim() != 2:
+            raise ValueError("corpus must be [N, D]")
+        self.corpus = corpus.to(dev).contiguous()
+        self.n, self.d = self.corpus.shape
+        self.id_offset = int(id_offset)
+        self.dtype_code = _lib.ARB_DTYPE_F32 if self.corpus.dtype == torch.float32 else _lib.ARB_DTYPE_BF16
+        self._ws = None
+
+    def _workspace(self, Q: int, k: int):
+        need = int(_lib.lib().arb_topk_search_workspace_bytes(self.dtype_code, Q, self.n, self.d, k))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = self._torch.empty(max(need, 256), dtype=self._torch.uint8, device=self.corpus.device)
+        return self._ws, need
+
+    def search(self, queries, k: int = 10, out_scores=None, out_ids=None):
+        """queries `[Q, D]` (same dtype family as the corpus; converted if not) ->
+        (scores float32 `[Q,k]`, ids int64 `[Q,k]`) as CUDA tensors, enqueued on the current stream."""
+        torch = self._torch
+        if isinstance(queries, np.ndarray):
+            queries = torch.from_numpy(np.ascontiguousarray(queries))
+        q = queries.to(self.corpus.device, non_blocking=True).to(self.corpus.dtype).contiguous()
+        if q.dim() != 2 or q.shape[1] != self.d:
+            raise ValueError(f"queries must be [Q, {self.d}]")
+        Q = q.shape[0]
+        if out_scores is None:
+            out_scores = torch.empty((Q, k), dtype=torch.float32, device=q.device)
+        if out_ids is None:
+            out_ids = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+        if Q == 0:
+            return out_scores, out_ids
+        if self.n == 0:
+            out_scores.fill_(float("-inf"))
+            out_ids.fill_(-1)
+            return out_scores, out_ids
+        ws, need = self._workspace(Q, k)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().arb_topk_search(_lib.ptr(q), _lib.ptr(self.corpus), self.dtype_code, Q,
+                                                  self.n, self.d, k, _lib.ptr(out_scores), _lib.ptr(out_ids),
+                                                  self.id_offset, _lib.ptr(ws), ws.numel(),
+                                                  _lib.current_stream()))
+        return out_scores, out_ids
+
+    @property
+    def launches_per_search(self) -> int:
+        return int(_lib.lib().arb_topk_search_launches(self.dtype_code))
+
+
+def merge_topk(scores, ids, out_scores=None, out_ids=None):
+    """Merge `[G,Q,k]` sorted lists (score desc, id asc) into `[Q,k]` on the GPU."""
+    torch = _torch()
+    G, Q, k = scores.shape
+    scores = scores.contiguous()
+    ids = ids.contiguous()
+    if out_scores is None:
+        out_scores = torch.empty((Q, k), dtype=torch.float32, device=scores.device)
+    if out_ids is None:
+        out_ids = torch.empty((Q, k), dtype=torch.int64, device=scores.device)
+    if Q:
+        with torch.cuda.device(scores.device):
+            _lib.check(_lib.lib().arb_topk_merge(_lib.ptr(scores), _lib.ptr(ids), G, Q, k,
+                                                 _lib.ptr(out_scores), _lib.ptr(out_ids),
+                                                 _lib.current_stream()))
+    return out_scores, out_ids
+
+
+def search(queries, corpus, k: int = 10, return_numpy: bool = True):
+    """One-shot API: `search(queries[Q,D], corpus[N,D], k) -> (scores[Q,k] f32, ids[Q,k] i64)`."""
+    idx = CorpusIndex(corpus)
+    s, i = idx.search(queries, k)
+    if return_numpy:
+        return s.cpu().numpy(), i.cpu().numpy()
+    return s, i
+
+
+class ShardedCorpusIndex:
+    """Row-sharded corpus across the ranks of a torch.distributed process group.
+
+    Every rank holds rows `shard_bounds(N, world, rank)` and the full query batch; `search`
+    returns the identical global top-k on every rank: local fused top-k -> all_gather of the
+    `[Q,k]` (score, id) lists -> k-way merge. The only collective on the path is that all_gather.
+    """
+
+    def __init__(self, local_corpus, global_rows: int, group=None, device: int | None = None):
+        import torch.distributed as dist
+
+        self._dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        lo, hi = shard_bounds(global_rows, self.world, self.rank)
+        n_local = local_corpus.shape[0]
+        if n_local != hi - lo:
+            raise ValueError(f"rank {self.rank}: local shard has {n_local} rows, expected {hi - lo}")
+        self.index = CorpusIndex(local_corpus, id_offset=lo, device=device)
+
+    def search(self, queries, k: int = 10):
+        torch = self.index._torch
+        ls, li = self.index.search(queries, k)
+        if self.world == 1:
+            return ls, li
+        gs = torch.empty((self.world,) + tuple(ls.shape), dtype=ls.dtype, device=ls.device)
+        gi = torch.empty((self.world,) + tuple(li.shape), dtype=li.dtype, device=li.device)
+        self._dist.all_gather_into_tensor(gs, ls, group=self.group)
+        self._dist.all_gather_into_tensor(gi, li, group=self.group)
+        return merge_topk(gs, gi)

@@ -1,0 +1,142 @@
+"""MPNet weights: config, HF-state-dict -> C-ABI struct packing, and a seeded synthetic generator.
+
+There are no all-mpnet-base-v2 weights offline, so "all-mpnet-base-v2" here means
+architecture- and shape-identical with seeded synthetic weights; `from_state_dict` accepts a real
+`transformers.MPNetModel.state_dict()` unchanged when one is available.
+Parameter names follow transformers' MPNetModel (modeling_mpnet.py:57-96, 116-273, 284-291).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+
+@dataclass(frozen=True)
+class MPNetArch:
+    """Published all-mpnet-base-v2 architecture (config.json + sentence_bert_config.json)."""
+
+    vocab_size: int = 30527
+    max_position_embeddings: int = 514
+    hidden_size: int = 768
+    num_layers: int = 12
+    num_heads: int = 12
+    intermediate_size: int = 3072
+    relative_attention_num_buckets: int = 32
+    pad_token_id: int = 1
+    layer_norm_eps: float = 1e-5
+    max_seq_length: int = 384
+
+    def c_struct(self, compute_dtype: int = _lib.ARB_DTYPE_BF16) -> _lib.MpnetConfig:
+        return _lib.MpnetConfig(self.vocab_size, self.max_position_embeddings, self.hidden_size,
+                                self.num_layers, self.num_heads, self.intermediate_size,
+                                self.relative_attention_num_buckets, self.pad_token_id,
+                                self.layer_norm_eps, compute_dtype)
+
+
+ALL_MPNET_BASE_V2 = MPNetArch()
+
+_LAYER_FIELDS = {
+    "q_w": "attention.attn.q.weight", "q_b": "attention.attn.q.bias",
+    "k_w": "attention.attn.k.weight", "k_b": "attention.attn.k.bias",
+    "v_w": "attention.attn.v.weight", "v_b": "attention.attn.v.bias",
+    "o_w": "attention.attn.o.weight", "o_b": "attention.attn.o.bias",
+    "attn_ln_g": "attention.LayerNorm.weight", "attn_ln_b": "attention.LayerNorm.bias",
+    "ffn_in_w": "intermediate.dense.weight", "ffn_in_b": "intermediate.dense.bias",
+    "ffn_out_w": "output.dense.weight", "ffn_out_b": "output.dense.bias",
+    "out_ln_g": "output.LayerNorm.weight", "out_ln_b": "output.LayerNorm.bias",
+}
+_TOP_FIELDS = {
+    "word_embeddings": "embeddings.word_embeddings.weight",
+    "position_embeddings": "embeddings.position_embeddings.weight",
+    "emb_ln_g": "embeddings.LayerNorm.weight",
+    "emb_ln_b": "embeddings.LayerNorm.bias",
+    "relative_attention_bias": "encoder.relative_attention_bias.weight",
+}
+
+
+def _as_f32(x) -> np.ndarray:
+    if hasattr(x, "detach"):
+        x = x.detach().cpu().float().numpy()
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+class PackedWeights:
+    """Owns the fp32 host arrays and the ctypes structs that point into them."""
+
+    def __init__(self, arch: MPNetArch, state_dict: dict):
+        self.arch = arch
+        self._keep = []  # numpy arrays must outlive the structs
+
+        def fp(name: str, shape: tuple):
+            key = name if name in state_dict else "0.auto_model." + name
+            if key not in state_dict:
+                raise KeyError(f"state dict lacks '{name}'")
+            a = _as_f32(state_dict[key])
+            if tuple(a.shape) != shape:
+                raise ValueError(f"{name}: shape {a.shape}, expected {shape}")
+            self._keep.append(a)
+            return a.ctypes.data_as(C.POINTER(C.c_float))
+
+        H, I = arch.hidden_size, arch.intermediate_size
+        shapes = {
+            "q_w": (H, H), "k_w": (H, H), "v_w": (H, H), "o_w": (H, H),
+            "q_b": (H,), "k_b": (H,), "v_b": (H,), "o_b": (H,),
+            "attn_ln_g": (H,), "attn_ln_b": (H,), "out_ln_g": (H,), "out_ln_b": (H,),
+            "ffn_in_w": (I, H), "ffn_in_b": (I,), "ffn_out_w": (H, I), "ffn_out_b": (H,),
+        }
+        self.layers = (_lib.MpnetLayerWeights * arch.num_layers)()
+        for l in range(arch.num_layers):
+            for field, suffix in _LAYER_FIELDS.items():
+                setattr(self.layers[l], field, fp(f"encoder.layer.{l}.{suffix}", shapes[field]))
+        self.struct = _lib.MpnetWeights()
+        top_shapes = {
+            "word_embeddings": (arch.vocab_size, H),
+            "position_embeddings": (arch.max_position_embeddings, H),
+            "emb_ln_g": (H,), "emb_ln_b": (H,),
+            "relative_attention_bias": (arch.relative_attention_num_buckets, arch.num_heads),
+        }
+        for field, name in _TOP_FIELDS.items():
+            setattr(self.struct, field, fp(name, top_shapes[field]))
+        self.struct.layers = C.cast(self.layers, C.POINTER(_lib.MpnetLayerWeights))
+
+
+def synthetic_state_dict(arch: MPNetArch = ALL_MPNET_BASE_V2, seed: int = 0) -> dict:
+    """Seeded random weights with the statistics of a trained encoder's parameter classes:
+    N(0, 0.02) matrices/embeddings (HF init), and NON-trivial biases, LayerNorm gamma/beta and
+    relative-position table so that bias/affine bugs cannot hide (SURVEY.md §7 'hard parts').
+    Returned as {HF parameter name: float32 numpy array}."""
+    rng = np.random.default_rng(seed)
+    H, I = arch.hidden_size, arch.intermediate_size
+
+    def mat(*shape, std=0.02):
+        return (rng.standard_normal(shape, dtype=np.float32) * std).astype(np.float32)
+
+    sd = {
+        "embeddings.word_embeddings.weight": mat(arch.vocab_size, H),
+        "embeddings.position_embeddings.weight": mat(arch.max_position_embeddings, H),
+        "embeddings.LayerNorm.weight": 1.0 + mat(H, std=0.1),
+        "embeddings.LayerNorm.bias": mat(H, std=0.1),
+        "encoder.relative_attention_bias.weight": mat(arch.relative_attention_num_buckets, arch.num_heads, std=0.5),
+    }
+    # HF zeroes the padding rows of both embedding tables
+    sd["embeddings.word_embeddings.weight"][arch.pad_token_id] = 0.0
+    sd["embeddings.position_embeddings.weight"][arch.pad_token_id] = 0.0
+    for l in range(arch.num_layers):
+        p = f"encoder.layer.{l}."
+        for nm in ("q", "k", "v", "o"):
+            # trained attention projections are O(1/sqrt(H))-scaled: use that so softmax is not flat
+            sd[p + f"attention.attn.{nm}.weight"] = mat(H, H, std=0.04)
+            sd[p + f"attention.attn.{nm}.bias"] = mat(H, std=0.05)
+        sd[p + "attention.LayerNorm.weight"] = 1.0 + mat(H, std=0.1)
+        sd[p + "attention.LayerNorm.bias"] = mat(H, std=0.1)
+        sd[p + "intermediate.dense.weight"] = mat(I, H, std=0.04)
+        sd[p + "intermediate.dense.bias"] = mat(I, std=0.05)
+        sd[p + "output.dense.weight"] = mat(H, I, std=0.04)
+        sd[p + "output.dense.bias"] = mat(H, std=0.05)
+        sd[p + "output.LayerNorm.weight"] = 1.0 + mat(H, std=0.1)
+        sd[p + "output.LayerNorm.bias"] = mat(H, std=0.1)
+    return sd

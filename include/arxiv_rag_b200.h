@@ -1,0 +1,150 @@
+/*
+ * arxiv_rag_b200 — C ABI of the B200-native retrieval hot path.
+ *
+ * This is the drop-in boundary for the ONE data-parallel path of matiasrodlo/arxiv-rag that
+ * BASELINE.json's north_star names:
+ *   stage A  batched all-mpnet-base-v2 encode: token ids -> MPNet encoder -> masked mean-pool
+ *            -> L2 normalise.  Replaces what `model.encode(batch, normalize_embeddings=True,
+ *            convert_to_numpy=True)` computes at
+ *            4-embed/generation/generate_embeddings_parallel.py:146-153 (and :160-165), i.e.
+ *            sentence-transformers -> transformers MPNetModel.forward (modeling_mpnet.py:403-455).
+ *   stage B  exact cosine top-k of query embeddings against the chunk-embedding matrix.  The
+ *            reference has no such routine; the definition generalised is
+ *            TextChunker._cosine_similarity, 3-chunks/pipeline/src/processors/text_processor.py:1601-1605,
+ *            with top_k from 3-chunks/pipeline/config.yaml:62-64.
+ *
+ * The reference is pure Python, so the binding a maintainer adds is a ctypes stub.
+ * Conventions: every function returns 0 on success or a negative ARB_ERR_* code; the message is
+ * available from arb_last_error().  No exceptions cross the boundary.  The caller owns every
+ * input/output buffer; "dev" pointers are CUDA device pointers on the current device, "host"
+ * pointers are ordinary host memory.  All work is enqueued on the given stream (a cudaStream_t
+ * passed as void*, NULL = legacy default stream) and the call returns after enqueue.
+ * There is no CPU fallback: without an sm_100a device every compute entry point fails.
+ */
+#ifndef ARXIV_RAG_B200_H
+#define ARXIV_RAG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARB_OK 0
+#define ARB_ERR_INVALID (-1)     /* bad shape / dtype / alignment / null pointer */
+#define ARB_ERR_CUDA (-2)        /* a CUDA call failed */
+#define ARB_ERR_WORKSPACE (-3)   /* caller workspace too small */
+#define ARB_ERR_UNSUPPORTED (-4)
+
+#define ARB_DTYPE_F32 0
+#define ARB_DTYPE_BF16 1
+#define ARB_DTYPE_F16 2
+
+#define ARB_EPI_BIAS 0
+#define ARB_EPI_BIAS_GELU 1
+#define ARB_EPI_BIAS_RESIDUAL 2
+
+/* Thread-local message of the last failing call on this thread. */
+const char* arb_last_error(void);
+/* ABI version of this header (bumped on any signature change). */
+int arb_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage A — MPNet sentence encoder (replaces SentenceTransformer('all-mpnet-base-v2').encode,
+ * generate_embeddings_parallel.py:47,146-153; math: modeling_mpnet.py:57-96,116-186,189-273,
+ * 284-360,403-455 + sentence-transformers Pooling(mean) + Normalize).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ArbMpnetConfig {
+    int32_t vocab_size;                     /* 30527 */
+    int32_t max_position_embeddings;        /* 514 */
+    int32_t hidden_size;                    /* 768 */
+    int32_t num_layers;                     /* 12 */
+    int32_t num_heads;                      /* 12 */
+    int32_t intermediate_size;              /* 3072 */
+    int32_t relative_attention_num_buckets; /* 32 */
+    int32_t pad_token_id;                   /* 1 (MPNetEmbeddings.padding_idx, modeling_mpnet.py:60) */
+    float layer_norm_eps;                   /* 1e-5 for all-mpnet-base-v2 */
+    int32_t compute_dtype;                  /* ARB_DTYPE_BF16 (BASELINE config) or ARB_DTYPE_F16:
+                                               16-bit format of weights + activations in HBM and
+                                               of the tensor-core operands; accumulation, softmax
+                                               and LayerNorm statistics are always fp32 */
+} ArbMpnetConfig;
+
+/* All pointers are HOST fp32 arrays in the nn.Module layouts ([out,in] for Linear weights). */
+typedef struct ArbMpnetLayerWeights {
+    const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b; /* attention.attn.{q,k,v,o} */
+    const float *attn_ln_g, *attn_ln_b;                         /* attention.LayerNorm */
+    const float *ffn_in_w, *ffn_in_b;                           /* intermediate.dense [I,H] */
+    const float *ffn_out_w, *ffn_out_b;                         /* output.dense [H,I] */
+    const float *out_ln_g, *out_ln_b;                           /* output.LayerNorm */
+} ArbMpnetLayerWeights;
+
+typedef struct ArbMpnetWeights {
+    const float* word_embeddings;         /* [vocab, H] */
+    const float* position_embeddings;     /* [max_pos, H] */
+    const float *emb_ln_g, *emb_ln_b;     /* embeddings.LayerNorm */
+    const float* relative_attention_bias; /* encoder.relative_attention_bias.weight [buckets, heads] */
+    const ArbMpnetLayerWeights* layers;   /* [num_layers] */
+} ArbMpnetWeights;
+
+/* Uploads and packs the weights (16-bit, fused QKV) and allocates activations for up to
+ * max_tokens = B*S tokens per call on CUDA device `device`. */
+int arb_mpnet_create(const ArbMpnetConfig* cfg, const ArbMpnetWeights* weights, int64_t max_tokens,
+                     int32_t max_seq, int32_t device, void** handle);
+int arb_mpnet_destroy(void* handle);
+/* Bytes of device memory held by the handle (weights + activations). */
+int64_t arb_mpnet_device_bytes(void* handle);
+/* ids/mask: dev int32 [B,S] (mask 1 = token, 0 = padding; ids of padding = pad_token_id);
+ * out: dev fp32 [B,hidden] unit-norm rows in input order. Rows whose mask is all zero -> 0. */
+int arb_mpnet_encode(void* handle, const int32_t* ids_dev, const int32_t* mask_dev, int32_t B,
+                     int32_t S, float* out_dev, void* stream);
+/* Number of kernel launches one arb_mpnet_encode call enqueues (for launch accounting). */
+int arb_mpnet_launches_per_encode(void* handle);
+/* MPNetEncoder.relative_position_bucket (modeling_mpnet.py:343-360) for relative_position = j-i. */
+int arb_mpnet_relative_bucket(int32_t relative_position, int32_t num_buckets, int32_t max_distance);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage B — exact cosine top-k search over unit-norm rows.
+ * scores[q, r] = <queries[q], corpus[id]>, rows ordered by (score desc, id asc);
+ * out_ids = local row + id_offset (int64), unused slots (k > N) hold score -inf / id -1.
+ * dtype ARB_DTYPE_BF16: operands bf16, scores accumulate bf16 products exactly in fp32.
+ * dtype ARB_DTYPE_F32 : operands fp32, scored via a 3-term bf16 split and re-scored in fp32.
+ * ------------------------------------------------------------------------------------------ */
+size_t arb_topk_search_workspace_bytes(int32_t dtype, int64_t Q, int64_t N, int32_t D, int32_t k);
+int arb_topk_search(const void* queries_dev, const void* corpus_dev, int32_t dtype, int64_t Q,
+                    int64_t N, int32_t D, int32_t k, float* out_scores_dev, int64_t* out_ids_dev,
+                    int64_t id_offset, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Merge G sorted per-shard lists (e.g. the all-gathered [G,Q,k] of a row-sharded corpus). */
+int arb_topk_merge(const float* scores_dev, const int64_t* ids_dev, int32_t G, int64_t Q, int32_t k,
+                   float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+/* Number of kernel launches one arb_topk_search call enqueues. */
+int arb_topk_search_launches(int32_t dtype);
+
+/* ------------------------------------------------------------------------------------------
+ * Kernel-level entry points (each is one launch); used by the parity tests and available to
+ * callers that want to compose the encoder themselves. All pointers are device pointers;
+ * `dtype` is the 16-bit activation format (ARB_DTYPE_BF16 or ARB_DTYPE_F16).
+ * ------------------------------------------------------------------------------------------ */
+/* C[M,N] = epi(A[M,K] . B[N,K]^T + bias[N]) (+ R[M,N]); 16-bit operands, fp32 accumulate. */
+int arb_gemm16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+               const float* bias, const void* R, int64_t ldr, int64_t M, int32_t N, int32_t K,
+               int32_t epilogue, int32_t dtype, void* stream);
+int arb_gemm16_f32out(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                      int64_t M, int32_t N, int32_t K, int32_t dtype, void* stream);
+int arb_embed_layernorm(const int32_t* ids, const float* word_emb, const float* pos_emb,
+                        const float* gamma, const float* beta, void* out16, int32_t B, int32_t S,
+                        int32_t H, int32_t vocab, int32_t max_pos, int32_t pad_id, float eps,
+                        int32_t dtype, void* stream);
+int arb_layernorm16(const void* x, const float* gamma, const float* beta, void* out, int64_t rows,
+                    int32_t H, float eps, int32_t dtype, void* stream);
+int arb_attention16(const void* qkv, const float* rel_bias, int32_t max_rel, const int32_t* mask,
+                    void* ctx, int32_t B, int32_t S, int32_t heads, int32_t head_dim, int32_t dtype,
+                    void* stream);
+int arb_pool_normalize(const void* hidden16, const int32_t* mask, float* out, int32_t B, int32_t S,
+                       int32_t H, int32_t dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARXIV_RAG_B200_H */

@@ -1,0 +1,109 @@
+"""CPU: pin the encode oracle — transformers.MPNetModel vs the plain-torch
+restatement vs the committed golden fixtures; position ids, relative buckets, pooling edges."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from arxiv_rag_b200.weights import ALL_MPNET_BASE_V2, MPNetArch, synthetic_state_dict
+from oracle import encode_oracle as eo
+from tests.conftest import GOLDEN
+
+
+def _arch_from_fixture(fx) -> MPNetArch:
+    a = fx["arch"].tolist()
+    return MPNetArch(vocab_size=a[0], max_position_embeddings=a[1], hidden_size=a[2], num_layers=a[3],
+                     num_heads=a[4], intermediate_size=a[5], relative_attention_num_buckets=a[6],
+                     pad_token_id=a[7], layer_norm_eps=float(fx["layer_norm_eps"]))
+
+
+@pytest.mark.parametrize("name", ["encode_tiny_2layer.npz", "encode_mpnet_base_b4_s32.npz"])
+def test_restatement_matches_golden(name):
+    """The golden vectors were produced by transformers.MPNetModel; the independent restatement
+    must reproduce them from the seed alone (fp32, tolerance 2e-6 abs on unit vectors)."""
+    fx = np.load(os.path.join(GOLDEN, name))
+    arch = _arch_from_fixture(fx)
+    sd = synthetic_state_dict(arch, int(fx["weight_seed"]))
+    emb, hidden = eo.restated_forward(arch, sd, fx["ids"], fx["mask"], return_hidden=True)
+    assert np.abs(emb - fx["embeddings"]).max() < 2e-6
+    valid = fx["mask"][0].astype(bool)
+    assert np.abs(hidden[0][valid] - fx["hidden_row0"][valid]).max() < 2e-4
+    assert np.allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-6)
+
+
+def test_transformers_matches_golden_tiny():
+    """Re-run the reference dependency itself and compare with the committed vectors."""
+    fx = np.load(os.path.join(GOLDEN, "encode_tiny_2layer.npz"))
+    arch = _arch_from_fixture(fx)
+    sd = synthetic_state_dict(arch, int(fx["weight_seed"]))
+    model = eo.reference_model(arch, sd)
+    emb = eo.oracle_encode(model, fx["ids"], fx["mask"])
+    assert np.abs(emb - fx["embeddings"]).max() < 1e-6
+
+
+def test_synthetic_tokens_match_golden():
+    fx = np.load(os.path.join(GOLDEN, "encode_tiny_2layer.npz"))
+    ids, mask = eo.synthetic_tokens(3, 16, vocab_size=1000, seed=int(fx["token_seed"]))
+    assert (ids == fx["ids"]).all() and (mask == fx["mask"]).all()
+    # §8d conventions: <s>=0 first, </s>=2 last valid, pad=1, a full row and a 1-token row
+    assert (ids[:, 0] == 0).all()
+    assert mask[0].sum() == 16 and mask[1].sum() == 1
+    assert (ids[mask == 0] == 1).all()
+
+
+def test_position_ids_and_buckets_against_transformers():
+    from transformers.models.mpnet.modeling_mpnet import MPNetEncoder, create_position_ids_from_input_ids
+
+    ids, _ = eo.synthetic_tokens(5, 23, seed=3)
+    t = torch.from_numpy(ids).long()
+    assert torch.equal(eo.position_ids_from_input_ids(t, 1), create_position_ids_from_input_ids(t, 1))
+    rel = torch.arange(-520, 521)
+    assert torch.equal(eo.relative_position_bucket(rel), MPNetEncoder.relative_position_bucket(rel))
+
+
+def test_c_abi_relative_bucket_matches_transformers(lib):
+    """The library expands the bucketed bias on the host; its bucket function must agree with
+    MPNetEncoder.relative_position_bucket (modeling_mpnet.py:343-360) for every offset."""
+    from transformers.models.mpnet.modeling_mpnet import MPNetEncoder
+
+    rel = torch.arange(-767, 768)
+    ref = MPNetEncoder.relative_position_bucket(rel, num_buckets=32, max_distance=128).tolist()
+    got = [lib.arb_mpnet_relative_bucket(int(r), 32, 128) for r in rel.tolist()]
+    assert got == ref
+
+
+def test_pooling_edges():
+    tok = torch.randn(3, 5, 8)
+    mask = torch.tensor([[1, 1, 1, 1, 1], [1, 0, 0, 0, 0], [0, 0, 0, 0, 0]])
+    e = eo.pool_normalize(tok, mask)
+    assert torch.allclose(e[0], torch.nn.functional.normalize(tok[0].mean(0), dim=0), atol=1e-6)
+    assert torch.allclose(e[1], torch.nn.functional.normalize(tok[1, 0], dim=0), atol=1e-6)
+    assert torch.equal(e[2], torch.zeros(8))  # all-pad row -> zero vector, not NaN
+
+
+def test_padding_does_not_change_valid_rows():
+    """Pad-to-longest per batch (sentence-transformers) must not change a row's embedding."""
+    arch = MPNetArch(vocab_size=1000, num_layers=2)
+    sd = synthetic_state_dict(arch, 0)
+    ids, mask = eo.synthetic_tokens(3, 12, vocab_size=1000, seed=9)
+    a = eo.restated_forward(arch, sd, ids, mask)
+    ids2 = np.concatenate([ids, np.ones((3, 7), np.int32)], 1)
+    mask2 = np.concatenate([mask, np.zeros((3, 7), np.int32)], 1)
+    b = eo.restated_forward(arch, sd, ids2, mask2)
+    assert np.abs(a - b).max() < 2e-6
+
+
+def test_bf16_rounding_budget_documented():
+    """DESIGN.md 'Numerics': simulate the CUDA path's 16-bit storage points on CPU. fp16 holds
+    cosine >= 0.9999 on every row; bf16 holds it on long rows and >= 0.9995 on the 1-token row."""
+    arch = MPNetArch(vocab_size=1000, num_layers=12)
+    sd = synthetic_state_dict(arch, 0)
+    ids, mask = eo.synthetic_tokens(4, 48, vocab_size=1000, seed=3)
+    ref = eo.restated_forward(arch, sd, ids, mask)
+    f16 = eo.restated_forward(arch, sd, ids, mask, round_fn=lambda x: x.to(torch.float16).float())
+    b16 = eo.restated_forward(arch, sd, ids, mask, round_fn=eo.bf16_round)
+    assert (f16 * ref).sum(1).min() >= 0.9999
+    cos_b = (b16 * ref).sum(1)
+    assert cos_b[0] >= 0.9999  # full-length row
+    assert cos_b.min() >= 0.9995
