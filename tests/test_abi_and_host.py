@@ -1,0 +1,179 @@
+"""CPU: the C-ABI library loads and exports every symbol include/*.h declares; error behaviour
+without a GPU; host-side logic (saved layouts, task split/reorder, sharding, gloo world_size 2)."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from arxiv_rag_b200 import _lib, generation, storage
+from arxiv_rag_b200.search import shard_bounds
+from tests.conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "arxiv_rag_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(arb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.arb_abi_version() == 1
+
+
+def test_struct_layout_matches_header():
+    # ArbMpnetConfig: 8 x int32, float, int32; layer weights: 16 pointers; weights: 6 pointers
+    assert C.sizeof(_lib.MpnetConfig) == 40
+    assert C.sizeof(_lib.MpnetLayerWeights) == 16 * C.sizeof(C.c_void_p)
+    assert C.sizeof(_lib.MpnetWeights) == 6 * C.sizeof(C.c_void_p)
+
+
+def test_argument_errors_return_codes_not_crashes(lib):
+    assert lib.arb_topk_search_workspace_bytes(_lib.ARB_DTYPE_BF16, 0, 10, 768, 10) == 0
+    assert lib.arb_topk_search_workspace_bytes(_lib.ARB_DTYPE_BF16, 128, 1_000_000, 768, 10) > 0
+    assert lib.arb_topk_search_workspace_bytes(7, 128, 1000, 768, 10) == 0
+    rc = lib.arb_topk_search(0, 0, _lib.ARB_DTYPE_BF16, 4, 4, 768, 10, 0, 0, 0, 0, 0, 0)
+    assert rc == -1 and b"null" in lib.arb_last_error()
+    rc = lib.arb_gemm16(0, 8, 0, 8, 0, 8, 0, 0, 0, 4, 32, 8, 0, _lib.ARB_DTYPE_BF16, 0)
+    assert rc == -1
+    rc = lib.arb_mpnet_encode(0, 0, 0, 1, 1, 0, 0)
+    assert rc == -1
+    with pytest.raises(_lib.ArbError):
+        _lib.check(rc)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from arxiv_rag_b200.encoder import B200SentenceEncoder
+    from arxiv_rag_b200.search import CorpusIndex
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        B200SentenceEncoder(None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        CorpusIndex(np.zeros((4, 8), np.float32))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "arxiv_rag_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+# ------------------------------------------------------------------ saved layouts
+def _chunks(n):
+    return [{"chunk_id": f"2101.{i:05d}_chunk_{i % 3}", "text": f"text {i} é", "metadata":
+             {"paper_id": f"2101.{i:05d}", "section": "intro", "quality_score": 0.9 + 0.001 * i}} for i in range(n)]
+
+
+def test_single_file_layout_matches_reference(tmp_path):
+    """generate_embeddings_parallel.py:271-321: float64 C-order matrix, metadata rows in order,
+    index.json keys."""
+    n = 7
+    rows = [np.random.default_rng(i).standard_normal(768).astype(np.float32) for i in range(n)]
+    storage.save_embeddings_to_disk_fallback(_chunks(n), rows, str(tmp_path))
+    arr = np.load(tmp_path / "embeddings.npy")
+    assert arr.dtype == np.float64 and arr.shape == (n, 768) and arr.flags.c_contiguous
+    assert np.array_equal(arr.astype(np.float32), np.stack(rows))  # values stay fp32-representable
+    meta = json.load(open(tmp_path / "metadata.json", encoding="utf-8"))
+    assert [m["chunk_id"] for m in meta] == [c["chunk_id"] for c in _chunks(n)]
+    assert set(meta[0]) == {"chunk_id", "paper_id", "section", "quality_score", "text", "text_length"}
+    assert meta[3]["text_length"] == len(_chunks(n)[3]["text"])
+    idx = json.load(open(tmp_path / "index.json"))
+    assert set(idx) == {"total_embeddings", "embedding_dimension", "total_size_gb"}
+    assert idx["total_embeddings"] == n and idx["embedding_dimension"] == 768
+    emb, meta2 = storage.load_embeddings_from_disk(str(tmp_path))
+    assert np.array_equal(emb, arr) and meta2 == meta
+
+
+def test_batched_layout_round_trip(tmp_path):
+    """save_embeddings_to_disk.py:15-117: batch files of `batch_size` rows, np.vstack on load."""
+    n = 25
+    rows = np.random.default_rng(0).standard_normal((n, 16)).astype(np.float32)
+    storage.save_embeddings_disk(_chunks(n), list(rows), str(tmp_path), batch_size=10)
+    assert sorted(p.name for p in tmp_path.glob("embeddings_batch_*.npy")) == [f"embeddings_batch_{i:04d}.npy" for i in range(3)]
+    idx = json.load(open(tmp_path / "index.json"))
+    assert idx["num_batches"] == 3 and idx["batch_size"] == 10 and len(idx["chunks"]) == n
+    emb, meta = storage.load_embeddings_from_disk(str(tmp_path))
+    assert emb.shape == (n, 16) and np.array_equal(emb.astype(np.float32), rows)
+    assert meta[12]["batch_index"] == 1 and meta[12]["batch_position"] == 2
+    e1, m1 = storage.load_embeddings_from_disk(str(tmp_path), batch_index=2)
+    assert e1.shape == (5, 16) and len(m1) == 5
+    assert storage.chunk_ids_of(meta)[24] == _chunks(n)[24]["chunk_id"]
+    storage.save_search_matrix(rows, str(tmp_path))
+    assert np.array_equal(np.asarray(storage.load_search_matrix(str(tmp_path))), rows)
+
+
+# ------------------------------------------------------------------ task split / sharding
+def test_task_split_and_reorder():
+    tasks = generation.split_tasks(1234, 500)
+    assert tasks == [(0, 0, 500), (1, 500, 1000), (2, 1000, 1234)]
+    assert generation.tasks_of_rank(tasks, 1, 2) == [(1, 500, 1000)]
+    res = {2: [np.full(2, 2.0)], 0: [np.full(2, 0.0), np.full(2, 0.5)], 1: [np.full(2, 1.0)]}
+    out = generation.reorder(res, 3)
+    assert [float(r[0]) for r in out] == [0.0, 0.5, 1.0, 2.0]
+    with pytest.raises(RuntimeError):
+        generation.reorder({0: [], 2: []}, 3)  # a missing task must not shift rows silently
+
+
+def test_shard_bounds_cover_exactly():
+    for n, g in [(10, 3), (5_000_000, 8), (7, 8), (0, 2)]:
+        spans = [shard_bounds(n, g, r) for r in range(g)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+
+
+_GLOO_WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["ARB_ROOT"])
+from arxiv_rag_b200.search import shard_bounds
+from arxiv_rag_b200 import generation
+from oracle import search_oracle as so
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# --- search protocol: shard rows, local top-k with id offsets, all_gather [G,Q,k], merge
+N, Q, D, k = 1001, 13, 32, 6
+c = so.synthetic_unit_rows(N, D, seed=0, plant_ties=True); q = so.synthetic_unit_rows(Q, D, seed=1)
+lo, hi = shard_bounds(N, world, rank)
+ls, li = so.oracle_search(q, c[lo:hi], k, id_offset=lo)
+gs = [torch.empty(Q, k) for _ in range(world)]; gi = [torch.empty(Q, k, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(gs, torch.from_numpy(ls)); dist.all_gather(gi, torch.from_numpy(li))
+ms, mi = so.merge_topk(torch.stack(gs).numpy(), torch.stack(gi).numpy())
+fs, fi = so.oracle_search(q, c, k)
+assert (mi == fi).all() and np.allclose(ms, fs, atol=1e-6), "sharded != unsharded"
+# --- encode protocol: round-robin tasks, all_gather_object, reorder (with a stub model)
+class Stub:
+    def encode(self, batch, **kw):
+        ids = batch[0]
+        return np.stack([np.full(4, float(r[0]), np.float32) for r in ids])
+generation._worker_model, generation._worker_model_name = Stub(), "all-mpnet-base-v2"
+chunks = [{"input_ids": [i, 5, 2]} for i in range(23)]
+rows = generation.generate_embeddings_parallel(chunks, batch_size=4, chunks_per_worker=5)
+assert len(rows) == 23 and [int(r[0]) for r in rows] == list(range(23)), "row order"
+dist.barrier()
+if rank == 0: print("GLOO_OK")
+"""
+
+
+def test_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, ARB_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert res.returncode == 0 and "GLOO_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]

@@ -1,0 +1,163 @@
+"""GPU: every kernel K0-K7 through the C ABI against a plain torch fp32 computation of the same
+op on seeded tensors (SURVEY.md §4 'kernel parity'). Tolerances are the 16-bit output rounding:
+bf16 2^-8 relative, fp16 2^-11; fp32 outputs 1e-5."""
+import math
+
+import pytest
+import torch
+
+from arxiv_rag_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+DT = {"bf16": (torch.bfloat16, _lib.ARB_DTYPE_BF16, 6e-3), "fp16": (torch.float16, _lib.ARB_DTYPE_F16, 8e-4)}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rel_err(got, ref):
+    return ((got.float() - ref.float()).abs().max() / ref.float().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (300, 256, 768), (1000, 768, 768), (513, 768, 3072),
+                                   (4096, 2304, 768), (1, 32, 8), (129, 96, 200)])
+def test_gemm_mainloop_fp32_out(lib, cuda, dt, shape):
+    """tcgen05 main loop alone: bf16/fp16 products are exact in fp32, only the summation order
+    differs -> 2e-5 of the output range. Covers ragged M, N < tile, K tail (TMA zero fill)."""
+    M, N, K = shape
+    tdt, code, _ = DT[dt]
+    torch.manual_seed(0)
+    A = (torch.randn(M, K, device=cuda) * 0.5).to(tdt)
+    B = (torch.randn(N, K, device=cuda) * 0.5).to(tdt)
+    C = torch.full((M, N), float("nan"), device=cuda)
+    _lib.check(lib.arb_gemm16_f32out(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, M, N, K, code, _stream()))
+    assert _rel_err(C, A.float() @ B.float().T) < 2e-5
+
+
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+@pytest.mark.parametrize("epi", [0, 1, 2])
+def test_gemm_epilogues(lib, cuda, dt, epi):
+    """bias (modeling_mpnet.py:145-159), bias+GELU(erf) (:225-228), bias+residual (:183,:239-243)."""
+    tdt, code, tol = DT[dt]
+    torch.manual_seed(1)
+    M, N, K = 777, 768, 768
+    A = (torch.randn(M, K, device=cuda) * 0.3).to(tdt)
+    B = (torch.randn(N, K, device=cuda) * 0.05).to(tdt)
+    bias = torch.randn(N, device=cuda)
+    R = torch.randn(M, N, device=cuda).to(tdt)
+    ref = A.float() @ B.float().T + bias
+    ref = [ref, torch.nn.functional.gelu(ref), ref + R.float()][epi]
+    C = torch.zeros(M, N, device=cuda, dtype=tdt)
+    _lib.check(lib.arb_gemm16(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, bias.data_ptr(),
+                              R.data_ptr() if epi == 2 else 0, N, M, N, K, epi, code, _stream()))
+    assert _rel_err(C, ref) < tol
+
+
+def test_gemm_strided_operands(lib, cuda):
+    """The encoder reads q|k|v column blocks and writes into wider buffers: lda/ldc > K/N."""
+    torch.manual_seed(2)
+    M, N, K = 500, 256, 128
+    Abig = (torch.randn(M, 3 * K, device=cuda)).to(torch.bfloat16)
+    B = (torch.randn(N, K, device=cuda) * 0.1).to(torch.bfloat16)
+    Cbig = torch.zeros(M, 2 * N, device=cuda)
+    A = Abig[:, K:2 * K]
+    _lib.check(lib.arb_gemm16_f32out(A.data_ptr(), 3 * K, B.data_ptr(), K, Cbig[:, N:].data_ptr(), 2 * N, M, N, K,
+                                     _lib.ARB_DTYPE_BF16, _stream()))
+    assert _rel_err(Cbig[:, N:], A.float() @ B.float().T) < 2e-5
+    assert (Cbig[:, :N] == 0).all()
+
+
+def test_gemm_rejects_bad_arguments(lib, cuda):
+    A = torch.zeros(8, 8, device=cuda, dtype=torch.bfloat16)
+    C = torch.zeros(8, 40, device=cuda)
+    assert lib.arb_gemm16_f32out(A.data_ptr(), 8, A.data_ptr(), 8, C.data_ptr(), 40, 8, 40, 8, _lib.ARB_DTYPE_BF16, _stream()) == -1
+    assert b"multiple of 32" in lib.arb_last_error()
+    assert lib.arb_gemm16_f32out(A.data_ptr(), 8, A.data_ptr(), 8, C.data_ptr(), 32, 8, 32, 8, 9, _stream()) == -1
+
+
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+@pytest.mark.parametrize("H,eps", [(768, 1e-5), (768, 1e-12), (384, 1e-5)])
+def test_layernorm(lib, cuda, dt, H, eps):
+    tdt, code, tol = DT[dt]
+    torch.manual_seed(3)
+    rows = 1003
+    x = (torch.randn(rows, H, device=cuda) * 3 + 0.5).to(tdt)
+    g = torch.randn(H, device=cuda) * 0.1 + 1
+    b = torch.randn(H, device=cuda) * 0.1
+    out = torch.zeros_like(x)
+    _lib.check(lib.arb_layernorm16(x.data_ptr(), g.data_ptr(), b.data_ptr(), out.data_ptr(), rows, H, eps, code, _stream()))
+    assert _rel_err(out, torch.nn.functional.layer_norm(x.float(), (H,), g, b, eps)) < tol
+
+
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+def test_embed_layernorm_and_position_ids(lib, cuda, dt):
+    """MPNetEmbeddings (modeling_mpnet.py:72-96) with create_position_ids_from_input_ids
+    (:889-897): pads keep position `padding_idx`, tokens count from padding_idx+1."""
+    tdt, code, tol = DT[dt]
+    torch.manual_seed(4)
+    B, S, V, P, H = 6, 70, 1000, 514, 768
+    ids = torch.randint(4, V, (B, S), device=cuda, dtype=torch.int32)
+    for r, ln in enumerate([70, 1, 20, 0, 69, 33]):
+        ids[r, ln:] = 1
+    ids[5, 10] = 1  # a pad id in the middle of a row: position counting must skip it
+    we = torch.randn(V, H, device=cuda) * 0.02
+    pe = torch.randn(P, H, device=cuda) * 0.02
+    g = torch.randn(H, device=cuda) * 0.1 + 1
+    b = torch.randn(H, device=cuda) * 0.1
+    out = torch.zeros(B * S, H, device=cuda, dtype=tdt)
+    _lib.check(lib.arb_embed_layernorm(ids.data_ptr(), we.data_ptr(), pe.data_ptr(), g.data_ptr(), b.data_ptr(),
+                                       out.data_ptr(), B, S, H, V, P, 1, 1e-5, code, _stream()))
+    m = (ids != 1).int()
+    pos = (torch.cumsum(m, 1) * m).long() + 1
+    ref = torch.nn.functional.layer_norm(we[ids.long()] + pe[pos], (H,), g, b, 1e-5).reshape(B * S, H)
+    assert _rel_err(out, ref) < tol
+
+
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+def test_pool_normalize(lib, cuda, dt):
+    """Pooling(mean) + Normalize: sum(mask*x)/clamp(sum mask,1e-9), x/max(||x||,1e-12); an
+    all-pad row gives the zero vector (not NaN); arbitrary (non-prefix) masks are honoured."""
+    tdt, code, _ = DT[dt]
+    torch.manual_seed(5)
+    B, S, H = 6, 50, 768
+    hid = torch.randn(B, S, H, device=cuda).to(tdt)
+    lens = torch.tensor([50, 1, 20, 0, 49, 7], device=cuda)
+    mask = (torch.arange(S, device=cuda)[None, :] < lens[:, None]).int().contiguous()
+    mask[5, 30] = 1
+    out = torch.full((B, H), float("nan"), device=cuda)
+    _lib.check(lib.arb_pool_normalize(hid.data_ptr(), mask.data_ptr(), out.data_ptr(), B, S, H, code, _stream()))
+    mm = mask.unsqueeze(-1).float()
+    e = (hid.float() * mm).sum(1) / torch.clamp(mm.sum(1), min=1e-9)
+    ref = torch.nn.functional.normalize(e, p=2, dim=1)
+    assert (out - ref).abs().max().item() < 1e-6
+    assert (out[3] == 0).all()
+
+
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+@pytest.mark.parametrize("case", [(3, 64, [64, 1, 17]), (4, 100, [100, 37, 0, 99]), (2, 384, [384, 200]), (1, 5, [3])])
+def test_attention(lib, cuda, dt, case):
+    """softmax(qk^T/8 + position_bias + (1-m)*finfo.min) v (modeling_mpnet.py:162-177); S not a
+    multiple of the 64-key block, 1-token rows and an all-masked row (uniform attention, as the
+    reference's fp32 arithmetic yields)."""
+    tdt, code, _ = DT[dt]
+    tol = 1.5e-2 if dt == "bf16" else 2e-3
+    B, S, lens = case
+    nH, dh, P = 12, 64, 512
+    H = nH * dh
+    torch.manual_seed(6)
+    qkv = torch.randn(B * S, 3 * H, device=cuda).to(tdt)
+    relb = torch.randn(nH, 2 * P - 1, device=cuda) * 0.5
+    mask = (torch.arange(S, device=cuda)[None, :] < torch.tensor(lens, device=cuda)[:, None]).int().contiguous()
+    ctx = torch.zeros(B * S, H, device=cuda, dtype=tdt)
+    _lib.check(lib.arb_attention16(qkv.data_ptr(), relb.data_ptr(), P, mask.data_ptr(), ctx.data_ptr(), B, S, nH, dh, code, _stream()))
+    q, k, v = [t.float().view(B, S, nH, dh).transpose(1, 2) for t in qkv.split(H, dim=1)]
+    idx = torch.arange(S, device=cuda)
+    bias = relb[:, idx[None, :] - idx[:, None] + (P - 1)]
+    ext = (1.0 - mask[:, None, None, :].float()) * torch.finfo(torch.float32).min
+    sc = q @ k.transpose(-1, -2) / math.sqrt(dh) + bias[None] + ext
+    ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * S, H)
+    assert torch.isfinite(ctx.float()).all()
+    assert _rel_err(ctx, ref) < tol
