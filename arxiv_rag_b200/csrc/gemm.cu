@@ -2,12 +2,27 @@
 // Replaces the nn.Linear calls of transformers' MPNet (modeling_mpnet.py:145-159 q/k/v,
 // :183 o, :225-228 intermediate+GELU, :239-243 output) that sentence-transformers' encode
 // reaches from generate_embeddings_parallel.py:146-153.
+//
+// Epilogue: 8 warps in two groups of 4 (one warp per TMEM lane quarter); group g owns columns
+// [g*BN/2, (g+1)*BN/2) of the tile. Per 128-byte-wide column chunk a thread pulls its row from
+// TMEM, applies bias / GELU / residual in fp32, writes the converted row into a swizzled staging
+// tile in shared memory, and one thread of the group issues a TMA store (coalesced, clipped at
+// the M/N edges). The residual chunk is TMA-loaded into the same staging tile beforehand, so
+// neither R nor C is ever touched with row-strided global accesses.
 #include "common.cuh"
 #include "kernels.h"
 #include "tmap.cuh"
 #include "umma_pipe.cuh"
 
 namespace arb {
+
+constexpr int kGemmBN = 256;
+constexpr int kGemmStages = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kGemmThreads = 64 + kEpiThreads;
+constexpr int kStageTileBytes = kBM * 128;  // one staging tile: 128 rows x 128 bytes
+using GemmSmem = PipeSmem<kGemmBN, kGemmStages, 2 * kStageTileBytes>;
 
 // Static persistent schedule: tile t -> (m-block t / num_n, n-block t % num_n) so the CTAs
 // running concurrently share A panels (activations) through L2 while B (weights) stays hot.
@@ -22,72 +37,111 @@ struct GemmTileIter {
     }
 };
 
-// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7), far below the 16-bit output rounding.
+// gelu(x) = x * Phi(x) with erf from Abramowitz-Stegun 7.1.28:
+//   1 - erf(z) = (1 + a1 z + ... + a6 z^6)^-16, |err| <= 3e-7, z = |x|/sqrt(2) folded into b_i.
+// One MUFU (rcp) and ~14 FMA-pipe ops per element; |gelu err| <= 8.2e-7 absolute in fp32.
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    p *= t;
-    const float e = exp2f(-z * z * 1.4426950408889634f);
-    const float erf_abs = fmaf(-p, e, 1.0f);
-    const float erf_v = copysignf(erf_abs, x);
-    return 0.5f * x * (1.0f + erf_v);
+    constexpr float b1 = 0.0705230784 / 1.4142135623730951;
+    constexpr float b2 = 0.0422820123 / 2.0;
+    constexpr float b3 = 0.0092705272 / 2.8284271247461903;
+    constexpr float b4 = 0.0001520143 / 4.0;
+    constexpr float b5 = 0.0002765672 / 5.656854249492381;
+    constexpr float b6 = 0.0000430638 / 8.0;
+    const float ax = fabsf(x);
+    float d = fmaf(ax, b6, b5);
+    d = fmaf(ax, d, b4);
+    d = fmaf(ax, d, b3);
+    d = fmaf(ax, d, b2);
+    d = fmaf(ax, d, b1);
+    d = fmaf(ax, d, 1.0f);
+    d *= d;
+    d *= d;
+    d *= d;
+    d *= d;                                  // d^16 (may overflow to +inf -> t = 0, correct limit)
+    float rcp;                               // single MUFU.RCP (1 ulp); rcp(+inf) = 0
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(d));
+    const float h = 0.5f * rcp;              // 0.5 * (1 - erf(|x|/sqrt2))
+    const float r = x >= 0.f ? 1.0f - h : h; // Phi(x)
+    return x * r;
 }
 
 // OutT = h16 (16-bit activations in the kF16 format) or float.
-template <int BN, int STAGES, int EPI, bool kF16, typename OutT>
-__global__ void __launch_bounds__(kPipeThreads, 1)
+template <int EPI, bool kF16, typename OutT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-              OutT* __restrict__ C, int64_t ldc, const float* __restrict__ bias,
-              const h16* __restrict__ R, int64_t ldr, int64_t M, int N, int K) {
+              const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
+              const float* __restrict__ bias, int64_t M, int N, int K) {
+    constexpr int BN = kGemmBN;
+    constexpr int CW = 128 / static_cast<int>(sizeof(OutT));  // columns per staging chunk
+    constexpr int CPG = (BN / 2) / CW;                        // chunks per group per tile
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // SWIZZLE_128B tiles need a 1024-byte aligned base; align by hand (the launcher adds slack).
-    PipeSmem<BN, STAGES> sm{smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)};
+    GemmSmem sm{smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)};
     const int warp = __shfl_sync(0xffffffff, threadIdx.x / 32, 0);
     const int lane = threadIdx.x & 31;
 
     const int num_m = static_cast<int>((M + kBM - 1) / kBM);
     const int num_n = (N + BN - 1) / BN;
     const int kblocks = (K + kBK - 1) / kBK;
-    GemmTileIter it{static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), num_m * num_n,
-                    num_n, BN};
+    GemmTileIter it{static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), num_m * num_n, num_n, BN};
 
-    const uint32_t tmem_base = pipe_setup(sm, warp, &tmap_a, &tmap_b);
+    const uint32_t tmem_base = pipe_setup(sm, warp, &tmap_a, &tmap_b, kEpiThreads);
 
     if (warp == 0) {
         if (elect_one()) pipe_produce(sm, &tmap_a, &tmap_b, it, kblocks, kEvictNormal, kEvictLast);
     } else if (warp == 1) {
-        if (elect_one()) pipe_mma<BN, STAGES, kF16>(sm, tmem_base, it, kblocks);
+        if (elect_one()) pipe_mma<GemmSmem, kF16>(sm, tmem_base, it, kblocks);
     } else {
-        // Epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32).
-        const int lane_grp = warp & 3;
+        const int ew = warp - 2;         // 0..7
+        const int grp = ew >> 2;         // column half owned by this warp's group
+        const int lane_grp = warp & 3;   // TMEM lanes [32*lane_grp, +32) are the only ones this warp may read
+        const int trow = lane_grp * 32 + lane;
+        const bool leader = (ew & 3) == 0 && lane == 0;  // issues the group's TMA traffic
+        uint8_t* stage_tile = sm.pre() + grp * kStageTileBytes;
+        uint8_t* my_row = stage_tile + trow * 128;
+        const int sw = trow & 7;
+        uint64_t* res_bar = sm.aux(grp);
+        uint32_t res_phase = 0;
+        if (leader) {
+            tma_prefetch_desc(&tmap_c);
+            if (EPI == EPI_BIAS_RESIDUAL) tma_prefetch_desc(&tmap_r);
+        }
         int acc = 0;
         uint32_t acc_phase = 0;
         int row_a, row_b;
         while (it.next(row_a, row_b)) {
             mbar_wait(sm.tmem_full(acc), acc_phase);
             tc_fence_after();
-            const int64_t row = static_cast<int64_t>(row_a) + lane_grp * 32 + lane;
-            const bool row_ok = row < M;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
-                                   static_cast<uint32_t>(acc * BN);
+                                   static_cast<uint32_t>(acc * BN + grp * (BN / 2));
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(taddr + c0, r);
+            for (int c = 0; c < CPG; ++c) {
+                const int col0 = row_b + grp * (BN / 2) + c * CW;
+                const bool live = col0 < N;  // group-uniform
+                if (EPI == EPI_BIAS_RESIDUAL && live && leader) {
+                    tma_store_wait_read<0>();  // the previous store has drained the staging tile
+                    mbar_arrive_expect_tx(res_bar, kStageTileBytes);
+                    tma_load_2d(&tmap_r, res_bar, stage_tile, col0, row_a, kEvictFirst);
+                }
+                uint32_t r[32 * (CW / 32)];
+#pragma unroll
+                for (int q = 0; q < CW / 32; ++q)
+                    tmem_ld_32x32(taddr + c * CW + q * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[q * 32]));
                 tmem_ld_wait();
-                const int col = row_b + c0;
-                if (col < N) {  // N % 32 == 0 is enforced by the launcher
-                    float v[32];
+                if (c == CPG - 1) {  // accumulator fully read by this thread: hand the buffer back
+                    tc_fence_before();
+                    mbar_arrive(sm.tmem_empty(acc));
+                }
+                if (!live) continue;
+                float v[CW];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (bias != nullptr) {
-                        const float4* bp = reinterpret_cast<const float4*>(bias + col);
+                for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
+                if (bias != nullptr) {
+                    // columns beyond N read zero bias via the clamp; they are clipped by the store
+                    const float4* bp = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < CW / 4; ++j) {
+                        if (col0 + 4 * j < N) {
                             const float4 b4 = __ldg(bp + j);
                             v[4 * j + 0] += b4.x;
                             v[4 * j + 1] += b4.y;
@@ -95,90 +149,99 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
                             v[4 * j + 3] += b4.w;
                         }
                     }
-                    if (EPI == EPI_BIAS_GELU) {
+                }
+                if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-                    }
-                    if (row_ok) {
-                        if (EPI == EPI_BIAS_RESIDUAL) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(R + row * ldr + col);
+                    for (int j = 0; j < CW; ++j) v[j] = gelu_erf(v[j]);
+                }
+                if (EPI == EPI_BIAS_RESIDUAL) {
+                    mbar_wait(res_bar, res_phase);
+                    res_phase ^= 1;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const uint4 u = __ldg(rp + j);
-                                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 u = *reinterpret_cast<const uint4*>(my_row + ((j ^ sw) << 4));
+                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const float2 f = unpack16x2<kF16>(w[q]);
-                                    v[8 * j + 2 * q] += f.x;
-                                    v[8 * j + 2 * q + 1] += f.y;
-                                }
-                            }
-                        }
-                        if constexpr (sizeof(OutT) == 2) {
-                            uint4* cp = reinterpret_cast<uint4*>(C + row * ldc + col);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                uint4 u;
-                                u.x = pack16x2<kF16>(v[8 * j + 0], v[8 * j + 1]);
-                                u.y = pack16x2<kF16>(v[8 * j + 2], v[8 * j + 3]);
-                                u.z = pack16x2<kF16>(v[8 * j + 4], v[8 * j + 5]);
-                                u.w = pack16x2<kF16>(v[8 * j + 6], v[8 * j + 7]);
-                                cp[j] = u;
-                            }
-                        } else {
-                            float4* cp = reinterpret_cast<float4*>(C + row * ldc + col);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                cp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2],
-                                                    v[4 * j + 3]);
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 f = unpack16x2<kF16>(w[q]);
+                            v[8 * j + 2 * q] += f.x;
+                            v[8 * j + 2 * q + 1] += f.y;
                         }
                     }
+                } else {
+                    if (leader) tma_store_wait_read<0>();
+                    named_bar_sync(1 + grp, 128);  // staging tile is free
+                }
+                if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        uint4 u;
+                        u.x = pack16x2<kF16>(v[8 * j + 0], v[8 * j + 1]);
+                        u.y = pack16x2<kF16>(v[8 * j + 2], v[8 * j + 3]);
+                        u.z = pack16x2<kF16>(v[8 * j + 4], v[8 * j + 5]);
+                        u.w = pack16x2<kF16>(v[8 * j + 6], v[8 * j + 7]);
+                        *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = u;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(my_row + ((j ^ sw) << 4)) =
+                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1 + grp, 128);  // every row of the staging tile is written
+                if (leader) {
+                    tma_store_2d(&tmap_c, stage_tile, col0, row_a);
+                    tma_store_commit();
                 }
             }
-            tc_fence_before();
-            mbar_arrive(sm.tmem_empty(acc));
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
             }
         }
+        if (leader) tma_store_wait<0>();
     }
     pipe_teardown(sm, warp, tmem_base);
 }
 
-template <int BN, int STAGES, int EPI, bool kF16, typename OutT>
+template <int EPI, bool kF16, typename OutT>
 static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb, OutT* C,
                             int64_t ldc, const float* bias, const h16* R, int64_t ldr, int64_t M,
                             int N, int K, cudaStream_t stream) {
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tc, tr;
     // the TMA element type only matters for OOB fill; both 16-bit formats move as raw 2-byte words
-    if (!make_tmap_bf16_k64(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K),
-                            static_cast<uint64_t>(lda), kBM) ||
-        !make_tmap_bf16_k64(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K),
-                            static_cast<uint64_t>(ldb), BN)) {
-        set_error("cuTensorMapEncodeTiled failed (A %p lda %lld, B %p ldb %lld)", (const void*)A,
-                  (long long)lda, (const void*)B, (long long)ldb);
+    bool ok = make_tmap_bf16_k64(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), kBM) &&
+              make_tmap_bf16_k64(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), kGemmBN) &&
+              make_tmap_rows128(&tc, C, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldc), sizeof(OutT));
+    if (ok) ok = make_tmap_rows128(&tr, EPI == EPI_BIAS_RESIDUAL ? static_cast<const void*>(R) : static_cast<const void*>(C),
+                                   static_cast<uint64_t>(M), static_cast<uint64_t>(N),
+                                   static_cast<uint64_t>(EPI == EPI_BIAS_RESIDUAL ? ldr : ldc),
+                                   EPI == EPI_BIAS_RESIDUAL ? 2 : static_cast<int>(sizeof(OutT)));
+    if (!ok) {
+        set_error("cuTensorMapEncodeTiled failed (A %p lda %lld, B %p ldb %lld, C %p ldc %lld)", (const void*)A,
+                  (long long)lda, (const void*)B, (long long)ldb, (const void*)C, (long long)ldc);
         return ARB_ERR_CUDA;
     }
-    auto kern = gemm16_kernel<BN, STAGES, EPI, kF16, OutT>;
-    constexpr int smem = PipeSmem<BN, STAGES>::kExtraOffset + 1024;  // +1024: alignment slack
+    auto kern = gemm16_kernel<EPI, kF16, OutT>;
+    constexpr int smem = GemmSmem::kExtraOffset + 1024;  // +1024: alignment slack
+    static_assert(smem <= 232448, "GEMM shared memory exceeds 227 KB");
     ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
+    const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + kGemmBN - 1) / kGemmBN);
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    kern<<<grid, kPipeThreads, smem, stream>>>(ta, tb, C, ldc, bias, R, ldr, M, N, K);
+    kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, tc, tr, bias, M, N, K);
     ARB_CHECK_CUDA(cudaGetLastError());
     return ARB_OK;
 }
 
 static int check_gemm_args(const void* A, int64_t lda, const void* B, int64_t ldb, const void* C,
-                           int64_t ldc, int64_t M, int N, int K) {
+                           int64_t ldc, int64_t M, int N, int K, int c_elt_bytes) {
     ARB_REQUIRE(A && B && C, "gemm: null operand");
     ARB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%lld N=%d K=%d", (long long)M, N, K);
-    ARB_REQUIRE(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
-    ARB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0,
-                "gemm: K/lda/ldb/ldc must be multiples of 8 (16-byte rows)");
-    ARB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+    ARB_REQUIRE(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
+    ARB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && (ldc * c_elt_bytes) % 16 == 0,
+                "gemm: K/lda/ldb must be multiples of 8 and C rows 16-byte multiples");
+    ARB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(C) & 15) == 0,
                 "gemm: operands must be 16-byte aligned");
     ARB_REQUIRE(M < (1ll << 31), "gemm: M too large");
@@ -191,16 +254,13 @@ static int dispatch_gemm16(const h16* A, int64_t lda, const h16* B, int64_t ldb,
                            int epilogue, cudaStream_t stream) {
     switch (epilogue) {
         case EPI_BIAS:
-            return launch_gemm_impl<256, 4, EPI_BIAS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr,
-                                                                 0, M, N, K, stream);
+            return launch_gemm_impl<EPI_BIAS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, stream);
         case EPI_BIAS_GELU:
-            return launch_gemm_impl<256, 4, EPI_BIAS_GELU, kF16, h16>(A, lda, B, ldb, C, ldc, bias,
-                                                                      nullptr, 0, M, N, K, stream);
+            return launch_gemm_impl<EPI_BIAS_GELU, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, stream);
         case EPI_BIAS_RESIDUAL:
             ARB_REQUIRE(R != nullptr && ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0,
                         "gemm: residual operand missing or misaligned");
-            return launch_gemm_impl<256, 4, EPI_BIAS_RESIDUAL, kF16, h16>(A, lda, B, ldb, C, ldc, bias,
-                                                                          R, ldr, M, N, K, stream);
+            return launch_gemm_impl<EPI_BIAS_RESIDUAL, kF16, h16>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, stream);
         default:
             set_error("gemm: unknown epilogue %d", epilogue);
             return ARB_ERR_INVALID;
@@ -210,7 +270,7 @@ static int dispatch_gemm16(const h16* A, int64_t lda, const h16* B, int64_t ldb,
 int launch_gemm16(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
                   const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
                   int epilogue, bool fp16, cudaStream_t stream) {
-    int rc = check_gemm_args(A, lda, B, ldb, C, ldc, M, N, K);
+    int rc = check_gemm_args(A, lda, B, ldb, C, ldc, M, N, K, 2);
     if (rc) return rc;
     ARB_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
                 "gemm: bias must be 16-byte aligned");
@@ -220,12 +280,10 @@ int launch_gemm16(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, 
 
 int launch_gemm16_f32out(const h16* A, int64_t lda, const h16* B, int64_t ldb, float* C,
                          int64_t ldc, int64_t M, int N, int K, bool fp16, cudaStream_t stream) {
-    int rc = check_gemm_args(A, lda, B, ldb, C, ldc, M, N, K);
+    int rc = check_gemm_args(A, lda, B, ldb, C, ldc, M, N, K, 4);
     if (rc) return rc;
-    return fp16 ? launch_gemm_impl<256, 4, EPI_BIAS, true, float>(A, lda, B, ldb, C, ldc, nullptr,
-                                                                  nullptr, 0, M, N, K, stream)
-                : launch_gemm_impl<256, 4, EPI_BIAS, false, float>(A, lda, B, ldb, C, ldc, nullptr,
-                                                                   nullptr, 0, M, N, K, stream);
+    return fp16 ? launch_gemm_impl<EPI_BIAS, true, float>(A, lda, B, ldb, C, ldc, nullptr, nullptr, 0, M, N, K, stream)
+                : launch_gemm_impl<EPI_BIAS, false, float>(A, lda, B, ldb, C, ldc, nullptr, nullptr, 0, M, N, K, stream);
 }
 
 }  // namespace arb

@@ -18,8 +18,8 @@
 namespace arb {
 
 constexpr int kSBN = 256;     // corpus rows per chunk (MMA N)
-constexpr int kMaxK = 128;    // sorted lists: 128 rows x k x 8 B of shared memory
-// smem ring depth: 3 x 48 KB stages when the lists need <= 64 KB (k <= 64), else 2 stages
+constexpr int kMaxK = 128;    // k <= 16: lists in registers; else 128 rows x k x 8 B of shared memory
+// smem ring depth: 4 x 48 KB stages for k <= 16, 3 when the lists need <= 64 KB, else 2
 
 struct SearchPlan {
     int nq;        // 128-query tiles
@@ -83,8 +83,11 @@ struct SearchTileIter {
     }
 };
 
-// Sorted insert into this thread's list (column `row` of the [k][128] arrays). Strict '<' keeps
-// earlier (smaller-id) entries ahead of equal scores: ids arrive in increasing order.
+constexpr int kSearchThreads = 192;  // TMA warp, MMA warp, 4 epilogue warps (one per TMEM lane quarter)
+
+// Sorted insert into this thread's shared-memory list (column `row` of the [k][128] arrays);
+// used for k > 16. Strict '<' keeps earlier (smaller-id) entries ahead of equal scores: ids
+// arrive in increasing order.
 __device__ __forceinline__ float list_insert(float* ls, int* li, int k, float v, int id) {
     int i = k - 1;
     while (i > 0 && ls[(i - 1) * kBM] < v) {
@@ -97,31 +100,51 @@ __device__ __forceinline__ float list_insert(float* ls, int* li, int k, float v,
     return ls[(k - 1) * kBM];
 }
 
-template <int kSStages>
-__global__ void __launch_bounds__(kPipeThreads, 1)
+// Register-resident sorted list (k <= KR <= 16): a branch-free carry chain, 5 instructions per
+// slot. A lane whose candidate does not beat its k-th best falls through unchanged, so the warp
+// runs the chain only when __any lane has a survivor. Strict '>' keeps equal scores in arrival
+// (= ascending id) order.
+template <int KR>
+__device__ __forceinline__ void reg_insert(float (&s)[KR], int (&id)[KR], float v, int nid) {
+#pragma unroll
+    for (int i = 0; i < KR; ++i) {
+        const bool p = v > s[i];
+        const float ts = s[i];
+        const int ti = id[i];
+        s[i] = p ? v : ts;
+        id[i] = p ? nid : ti;
+        v = p ? ts : v;
+        nid = p ? ti : nid;
+    }
+}
+
+// KR > 0: top-k lists in registers (k <= KR); KR == 0: lists in shared memory (k <= kMaxK).
+template <int kSStages, int KR>
+__global__ void __launch_bounds__(kSearchThreads, 1)
 search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                    const __grid_constant__ CUtensorMap tmap_c, float* __restrict__ part_scores,
                    int32_t* __restrict__ part_ids, int64_t Q, int64_t N, int D, int k, int nq, int cps,
                    int nchunks, int nsplit) {
+    using SM = PipeSmem<kSBN, kSStages>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    PipeSmem<kSBN, kSStages> sm{smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)};
+    SM sm{smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)};
     const int warp = __shfl_sync(0xffffffff, threadIdx.x / 32, 0);
     const int lane = threadIdx.x & 31;
     const int kblocks = (D + kBK - 1) / kBK;
     const int items = nq * nsplit;
     SearchTileIter it(static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), items, nq, cps, nchunks);
 
-    const uint32_t tmem_base = pipe_setup(sm, warp, &tmap_q, &tmap_c);
+    const uint32_t tmem_base = pipe_setup(sm, warp, &tmap_q, &tmap_c, 128);
 
     if (warp == 0) {
         // queries are re-read by every chunk -> keep in L2; the corpus streams through once per split
         if (elect_one()) pipe_produce(sm, &tmap_q, &tmap_c, it, kblocks, kEvictLast, kEvictNormal);
     } else if (warp == 1) {
-        if (elect_one()) pipe_mma<kSBN, kSStages, false>(sm, tmem_base, it, kblocks);
+        if (elect_one()) pipe_mma<SM, false>(sm, tmem_base, it, kblocks);
     } else {
         const int lane_grp = warp & 3;
         const int trow = lane_grp * 32 + lane;  // row of the 128-query tile owned by this thread
-        float* ls = reinterpret_cast<float*>(sm.extra()) + trow;                 // [k][128]
+        float* ls = reinterpret_cast<float*>(sm.extra()) + trow;                 // [k][128] (KR == 0)
         int* li = reinterpret_cast<int*>(sm.extra() + static_cast<size_t>(k) * kBM * 4) + trow;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -130,9 +153,19 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             const int qt = item % nq;
             const int c_begin = split * cps;
             const int c_end = min(c_begin + cps, nchunks);
-            for (int i = 0; i < k; ++i) {
-                ls[i * kBM] = -INFINITY;
-                li[i * kBM] = -1;
+            constexpr int KRA = KR > 0 ? KR : 1;
+            float rs[KRA];
+            int ri[KRA];
+#pragma unroll
+            for (int i = 0; i < KRA; ++i) {
+                rs[i] = -INFINITY;
+                ri[i] = -1;
+            }
+            if (KR == 0) {
+                for (int i = 0; i < k; ++i) {
+                    ls[i * kBM] = -INFINITY;
+                    li[i * kBM] = -1;
+                }
             }
             float thr = -INFINITY;
             for (int chunk = c_begin; chunk < c_end; ++chunk) {
@@ -147,18 +180,21 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     uint32_t r[32];
                     tmem_ld_32x32(taddr + c0, r);
                     tmem_ld_wait();
-                    if (c0 + 32 <= nvalid) {
+                    if (c0 >= nvalid) continue;  // warp-uniform: columns past the corpus end
+                    const bool full = c0 + 32 <= nvalid;
+                    const int id0 = static_cast<int>(n0) + c0;
+                    if (KR > 0) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float v = __uint_as_float(r[j]);
-                            if (v > thr) thr = list_insert(ls, li, k, v, static_cast<int>(n0) + c0 + j);
+                            float v = __uint_as_float(r[j]);
+                            if (!full && c0 + j >= nvalid) v = -INFINITY;
+                            if (__any_sync(0xffffffff, v > rs[KRA - 1])) reg_insert<KRA>(rs, ri, v, id0 + j);
                         }
-                    } else if (c0 < nvalid) {
+                    } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float v = __uint_as_float(r[j]);
-                            if (c0 + j < nvalid && v > thr)
-                                thr = list_insert(ls, li, k, v, static_cast<int>(n0) + c0 + j);
+                            if ((full || c0 + j < nvalid) && v > thr) thr = list_insert(ls, li, k, v, id0 + j);
                         }
                     }
                 }
@@ -174,9 +210,18 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             if (qrow < Q) {
                 float* ps = part_scores + (static_cast<int64_t>(split) * Q + qrow) * k;
                 int32_t* pi = part_ids + (static_cast<int64_t>(split) * Q + qrow) * k;
-                for (int i = 0; i < k; ++i) {
-                    ps[i] = ls[i * kBM];
-                    pi[i] = li[i * kBM];
+                if (KR > 0) {
+#pragma unroll
+                    for (int i = 0; i < KRA; ++i)
+                        if (i < k) {
+                            ps[i] = rs[i];
+                            pi[i] = ri[i];
+                        }
+                } else {
+                    for (int i = 0; i < k; ++i) {
+                        ps[i] = ls[i * kBM];
+                        pi[i] = li[i * kBM];
+                    }
                 }
             }
         }
@@ -295,17 +340,19 @@ int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int6
         set_error("search: cuTensorMapEncodeTiled failed");
         return ARB_ERR_CUDA;
     }
-    if (k <= 64) {
-        const int smem = PipeSmem<kSBN, 3>::kExtraOffset + k * kBM * 8 + 1024;
-        ARB_CHECK_CUDA(cudaFuncSetAttribute(search_topk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        search_topk_kernel<3><<<p.grid, kPipeThreads, smem, stream>>>(
-            tq, tc, part_scores, part_ids, Q, N, D, k, p.nq, p.cps, p.nchunks, p.nsplit);
-    } else {
-        const int smem = PipeSmem<kSBN, 2>::kExtraOffset + k * kBM * 8 + 1024;
-        ARB_CHECK_CUDA(cudaFuncSetAttribute(search_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        search_topk_kernel<2><<<p.grid, kPipeThreads, smem, stream>>>(
-            tq, tc, part_scores, part_ids, Q, N, D, k, p.nq, p.cps, p.nchunks, p.nsplit);
-    }
+    auto launch = [&](auto kern, int stages_bytes, int list_bytes) -> int {
+        const int smem = stages_bytes + list_bytes + 1024;
+        ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<p.grid, kSearchThreads, smem, stream>>>(tq, tc, part_scores, part_ids, Q, N, D, k, p.nq, p.cps,
+                                                       p.nchunks, p.nsplit);
+        return ARB_OK;
+    };
+    int lrc;
+    if (k <= 10) lrc = launch(search_topk_kernel<4, 10>, PipeSmem<kSBN, 4>::kExtraOffset, 0);
+    else if (k <= 16) lrc = launch(search_topk_kernel<4, 16>, PipeSmem<kSBN, 4>::kExtraOffset, 0);
+    else if (k <= 64) lrc = launch(search_topk_kernel<3, 0>, PipeSmem<kSBN, 3>::kExtraOffset, k * kBM * 8);
+    else lrc = launch(search_topk_kernel<2, 0>, PipeSmem<kSBN, 2>::kExtraOffset, k * kBM * 8);
+    if (lrc) return lrc;
     ARB_CHECK_CUDA(cudaGetLastError());
     return launch_merge_impl<int32_t>(part_scores, part_ids, p.nsplit, Q, k, id_offset, out_scores,
                                       out_ids, stream);

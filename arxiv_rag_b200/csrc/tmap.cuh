@@ -44,4 +44,22 @@ inline bool make_tmap_bf16_k64(CUtensorMap* map, const void* base, uint64_t rows
     return r == CUDA_SUCCESS;
 }
 
+// Output / residual tiles: row-major [rows, cols] with `elt_bytes`-wide elements; box =
+// [128 rows, 128 bytes of columns], 128-byte swizzle (the epilogue writes its staging tile with
+// the same XOR pattern). Out-of-bounds rows/columns are clipped on store and zero on load.
+inline bool make_tmap_rows128(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                              uint64_t ld, int elt_bytes) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * static_cast<uint64_t>(elt_bytes)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elt_bytes), 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                     2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 }  // namespace arb

@@ -1,9 +1,9 @@
 // Warp-specialised TMA -> smem ring -> tcgen05.mma -> TMEM pipeline shared by the encoder
-// GEMMs and the search score kernel. One CTA per SM, 6 warps:
+// GEMMs and the search score kernel. One CTA per SM:
 //   warp 0      TMA producer (one elected lane)
 //   warp 1      TMEM owner + MMA issuer (one elected lane)
-//   warps 2..5  epilogue: TMEM -> registers -> (bias/GELU/residual store | running top-k)
-// Tiles are 128 (M) x BN (N) x 64 (K-block); A and B are both K-major bf16, loaded with the
+//   warps 2..   epilogue: TMEM -> registers -> (bias/GELU/residual -> smem -> TMA store | top-k)
+// Tiles are 128 (M) x BN (N) x 64 (K-block); A and B are both K-major 16-bit, loaded with the
 // 128-byte swizzle. The fp32 accumulator is double buffered in TMEM (2 x BN columns) so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
@@ -13,63 +13,65 @@ namespace arb {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kPipeThreads = 192;
 
-template <int BN, int STAGES>
+// Shared-memory carve-up: [STAGES x (A tile | B tile)] [PRE bytes, 1024-aligned: epilogue staging]
+// [barriers] [extra...]
+template <int BN, int STAGES, int PRE = 0>
 struct PipeSmem {
+    static constexpr int kBN = BN;
+    static constexpr int kStages = STAGES;
     static constexpr int kABytes = kBM * kBK * 2;
     static constexpr int kBBytes = BN * kBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarOffset = STAGES * kStageBytes;
-    // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] + tmem base ptr
-    static constexpr int kBarBytes = (2 * STAGES + 4) * 8 + 16;
+    static constexpr int kPreOffset = STAGES * kStageBytes;
+    static constexpr int kBarOffset = kPreOffset + PRE;
+    // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] aux[2] + tmem base ptr
+    static constexpr int kNumBars = 2 * STAGES + 6;
+    static constexpr int kBarBytes = kNumBars * 8 + 16;
     static constexpr int kExtraOffset = kBarOffset + ((kBarBytes + 127) / 128) * 128;
 
     uint8_t* base;
     __device__ __forceinline__ uint8_t* a(int s) const { return base + s * kStageBytes; }
     __device__ __forceinline__ uint8_t* b(int s) const { return base + s * kStageBytes + kABytes; }
-    __device__ __forceinline__ uint64_t* full(int s) const {
-        return reinterpret_cast<uint64_t*>(base + kBarOffset) + s;
-    }
-    __device__ __forceinline__ uint64_t* empty(int s) const {
-        return reinterpret_cast<uint64_t*>(base + kBarOffset) + STAGES + s;
-    }
-    __device__ __forceinline__ uint64_t* tmem_full(int s) const {
-        return reinterpret_cast<uint64_t*>(base + kBarOffset) + 2 * STAGES + s;
-    }
-    __device__ __forceinline__ uint64_t* tmem_empty(int s) const {
-        return reinterpret_cast<uint64_t*>(base + kBarOffset) + 2 * STAGES + 2 + s;
-    }
+    __device__ __forceinline__ uint8_t* pre() const { return base + kPreOffset; }
+    __device__ __forceinline__ uint64_t* bars() const { return reinterpret_cast<uint64_t*>(base + kBarOffset); }
+    __device__ __forceinline__ uint64_t* full(int s) const { return bars() + s; }
+    __device__ __forceinline__ uint64_t* empty(int s) const { return bars() + STAGES + s; }
+    __device__ __forceinline__ uint64_t* tmem_full(int s) const { return bars() + 2 * STAGES + s; }
+    __device__ __forceinline__ uint64_t* tmem_empty(int s) const { return bars() + 2 * STAGES + 2 + s; }
+    __device__ __forceinline__ uint64_t* aux(int s) const { return bars() + 2 * STAGES + 4 + s; }
     __device__ __forceinline__ uint32_t* tmem_ptr() const {
-        return reinterpret_cast<uint32_t*>(base + kBarOffset + (2 * STAGES + 4) * 8);
+        return reinterpret_cast<uint32_t*>(base + kBarOffset + kNumBars * 8);
     }
     __device__ __forceinline__ uint8_t* extra() const { return base + kExtraOffset; }
 };
 
+template <int BN>
+__host__ __device__ constexpr uint32_t tmem_cols_for() {
+    return (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+}
+
 // Barrier init + TMEM allocation; returns the TMEM base address to every thread.
-template <int BN, int STAGES>
-__device__ __forceinline__ uint32_t pipe_setup(const PipeSmem<BN, STAGES>& sm, int warp,
-                                               const void* tmap_a, const void* tmap_b) {
-    constexpr uint32_t kTmemCols = (2 * BN <= 32)    ? 32
-                                   : (2 * BN <= 64)  ? 64
-                                   : (2 * BN <= 128) ? 128
-                                   : (2 * BN <= 256) ? 256
-                                                     : 512;
+// epi_threads = number of epilogue threads that arrive on tmem_empty per tile.
+template <class SM>
+__device__ __forceinline__ uint32_t pipe_setup(const SM& sm, int warp, const void* tmap_a,
+                                               const void* tmap_b, uint32_t epi_threads) {
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(tmap_a);
         tma_prefetch_desc(tmap_b);
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < SM::kStages; ++s) {
             mbar_init(sm.full(s), 1);
             mbar_init(sm.empty(s), 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(sm.tmem_full(s), 1);
-            mbar_init(sm.tmem_empty(s), 128);
+            mbar_init(sm.tmem_empty(s), epi_threads);
+            mbar_init(sm.aux(s), 1);
         }
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(sm.tmem_ptr(), kTmemCols);
+        tmem_alloc(sm.tmem_ptr(), tmem_cols_for<SM::kBN>());
         tmem_relinquish();
     }
     tc_fence_before();
@@ -78,38 +80,32 @@ __device__ __forceinline__ uint32_t pipe_setup(const PipeSmem<BN, STAGES>& sm, i
     return *sm.tmem_ptr();
 }
 
-template <int BN, int STAGES>
-__device__ __forceinline__ void pipe_teardown(const PipeSmem<BN, STAGES>& sm, int warp,
-                                              uint32_t tmem_base) {
-    constexpr uint32_t kTmemCols = (2 * BN <= 32)    ? 32
-                                   : (2 * BN <= 64)  ? 64
-                                   : (2 * BN <= 128) ? 128
-                                   : (2 * BN <= 256) ? 256
-                                                     : 512;
+template <class SM>
+__device__ __forceinline__ void pipe_teardown(const SM& sm, int warp, uint32_t tmem_base) {
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         __syncwarp();
-        tmem_dealloc(tmem_base, kTmemCols);
+        tmem_dealloc(tmem_base, tmem_cols_for<SM::kBN>());
     }
 }
 
 // Producer: for every tile the iterator yields, stream its K-blocks through the ring.
 // TileIter: bool next(int& row_a, int& row_b) — first rows of the A and B tiles.
-template <int BN, int STAGES, class TileIter>
-__device__ __forceinline__ void pipe_produce(const PipeSmem<BN, STAGES>& sm, const void* tmap_a,
-                                             const void* tmap_b, TileIter it, int kblocks,
-                                             uint64_t hint_a, uint64_t hint_b) {
+template <class SM, class TileIter>
+__device__ __forceinline__ void pipe_produce(const SM& sm, const void* tmap_a, const void* tmap_b,
+                                             TileIter it, int kblocks, uint64_t hint_a,
+                                             uint64_t hint_b) {
     int stage = 0;
     uint32_t phase = 0;
     int row_a, row_b;
     while (it.next(row_a, row_b)) {
         for (int kb = 0; kb < kblocks; ++kb) {
             mbar_wait(sm.empty(stage), phase ^ 1);
-            mbar_arrive_expect_tx(sm.full(stage), PipeSmem<BN, STAGES>::kStageBytes);
+            mbar_arrive_expect_tx(sm.full(stage), SM::kStageBytes);
             tma_load_2d(tmap_a, sm.full(stage), sm.a(stage), kb * kBK, row_a, hint_a);
             tma_load_2d(tmap_b, sm.full(stage), sm.b(stage), kb * kBK, row_b, hint_b);
-            if (++stage == STAGES) {
+            if (++stage == SM::kStages) {
                 stage = 0;
                 phase ^= 1;
             }
@@ -119,10 +115,9 @@ __device__ __forceinline__ void pipe_produce(const PipeSmem<BN, STAGES>& sm, con
 
 // MMA issuer: 4 x (128 x BN x 16) tcgen05.mma per K-block, accumulating in the TMEM buffer
 // that the epilogue has released; commits release the smem stage and publish the accumulator.
-template <int BN, int STAGES, bool kF16, class TileIter>
-__device__ __forceinline__ void pipe_mma(const PipeSmem<BN, STAGES>& sm, uint32_t tmem_base,
-                                         TileIter it, int kblocks) {
-    constexpr uint32_t idesc = umma_idesc_16bit(kBM, BN, kF16);
+template <class SM, bool kF16, class TileIter>
+__device__ __forceinline__ void pipe_mma(const SM& sm, uint32_t tmem_base, TileIter it, int kblocks) {
+    constexpr uint32_t idesc = umma_idesc_16bit(kBM, SM::kBN, kF16);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -131,7 +126,7 @@ __device__ __forceinline__ void pipe_mma(const PipeSmem<BN, STAGES>& sm, uint32_
     while (it.next(row_a, row_b)) {
         mbar_wait(sm.tmem_empty(acc), acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t tmem_d = tmem_base + acc * SM::kBN;
         for (int kb = 0; kb < kblocks; ++kb) {
             mbar_wait(sm.full(stage), phase);
             tc_fence_after();
@@ -143,7 +138,7 @@ __device__ __forceinline__ void pipe_mma(const PipeSmem<BN, STAGES>& sm, uint32_
                 umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit(sm.empty(stage));
-            if (++stage == STAGES) {
+            if (++stage == SM::kStages) {
                 stage = 0;
                 phase ^= 1;
             }
@@ -154,6 +149,10 @@ __device__ __forceinline__ void pipe_mma(const PipeSmem<BN, STAGES>& sm, uint32_
             acc_phase ^= 1;
         }
     }
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 }  // namespace arb
