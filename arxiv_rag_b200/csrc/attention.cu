@@ -4,10 +4,13 @@
 // position bias of MPNetEncoder.compute_position_bias (:324-360) and the additive mask
 // (1-m)*finfo.min of get_extended_attention_mask (modeling_utils.py:936-947).
 //
-// One CTA per (sequence, head): K and V of the head ([S,64] bf16 each) are staged once in
+// One CTA per (sequence, head): K and V of the head ([S,64] 16-bit each) are staged once in
 // shared memory (XOR-swizzled 16-byte chunks, conflict-free for ldmatrix); each warp then
-// runs a flash-style online softmax over 16-query-row blocks with bf16 mma.sync tiles and
-// fp32 statistics/accumulators.
+// runs a flash-style online softmax over 16-query-row blocks with mma.sync tiles and fp32
+// statistics/accumulators. The relative-position bias depends only on j-i, so a thread reads it
+// as one contiguous run of a padded table (rows g and g+8 share the run shifted by 8 keys).
+// Keys after the last unmasked key contribute exactly 0 in the reference's fp32 arithmetic, so
+// key blocks beyond it are skipped (unless the whole row is masked: uniform attention).
 #include "common.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -51,6 +54,11 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ float fast_exp2(float x) {  // single MUFU.EX2; exp2(-inf) = 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 template <bool kF16>
 __global__ void __launch_bounds__(kAttnThreads, 2)
@@ -59,10 +67,14 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
                  float scale_log2e) {
     extern __shared__ __align__(128) uint8_t smem_attn[];
     const int Spad = (S + 63) & ~63;
+    const int OFF = Spad + 16;                                // bias table: entry (j - i) + OFF
+    const int nbias = 2 * Spad + 32;
     uint8_t* sK = smem_attn;                                  // [Spad][128 B], swizzled
     uint8_t* sV = sK + static_cast<size_t>(Spad) * 128;       // [Spad][128 B], swizzled
-    float* sBias = reinterpret_cast<float*>(sV + static_cast<size_t>(Spad) * 128);  // [2S-1]
-    float* sMask = sBias + (2 * S - 1 + 3) / 4 * 4;           // [Spad] additive, log2 domain
+    float* sBias = reinterpret_cast<float*>(sV + static_cast<size_t>(Spad) * 128);  // [nbias], x log2e
+    float* sMask = sBias + nbias;                             // [Spad] additive, log2 domain
+    __shared__ int s_last;                                    // index of the last unmasked key, -1 if none
+    __shared__ int s_blk_clear[16];                           // per 64-key block: 1 = no masked / out-of-range key
 
     const int h = blockIdx.x, b = blockIdx.y;
     const int H = heads * kDH;
@@ -70,7 +82,9 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
     const h16* base = qkv + static_cast<int64_t>(b) * S * ld;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // ---- stage K, V (zero rows beyond S), bias slice and mask
+    // ---- stage K, V (zero rows beyond S), bias table and mask
+    if (tid == 0) s_last = -1;
+    if (tid < 16) s_blk_clear[tid] = 1;
     const uint32_t sK_u = smem_u32(sK), sV_u = smem_u32(sV);
     for (int idx = tid; idx < Spad * 16; idx += kAttnThreads) {
         const int r = idx >> 4, c = idx & 7, isv = (idx >> 3) & 1;
@@ -83,23 +97,49 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    for (int i = tid; i < 2 * S - 1; i += kAttnThreads) {
-        // entry i <-> relative position (j - i_q) = i - (S-1)
-        sBias[i] = rel_bias[static_cast<int64_t>(h) * (2 * max_rel - 1) + (i - (S - 1)) + (max_rel - 1)] * kLog2e;
+    for (int i = tid; i < nbias; i += kAttnThreads) {
+        const int rel = i - OFF;  // j - i_query
+        sBias[i] = (rel > -S && rel < S)
+                       ? rel_bias[static_cast<int64_t>(h) * (2 * max_rel - 1) + rel + (max_rel - 1)] * kLog2e
+                       : 0.f;
     }
+    __syncthreads();  // s_last initialised
+    int my_last = -1;
     for (int j = tid; j < Spad; j += kAttnThreads) {
         float m = -INFINITY;  // keys beyond the sequence never contribute
-        if (j < S) m = mask[static_cast<int64_t>(b) * S + j] != 0 ? 0.f : kMaskMin;
+        if (j < S) {
+            const bool on = mask[static_cast<int64_t>(b) * S + j] != 0;
+            m = on ? 0.f : kMaskMin;
+            if (on) my_last = j;
+        }
         sMask[j] = m;
+        if (m != 0.f) s_blk_clear[j >> 6] = 0;  // benign race: every writer stores 0
     }
+    if (my_last >= 0) atomicMax(&s_last, my_last);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+
+    // keys in (last, S) are masked: exactly zero probability unless every key is masked
+    const int kv_len = s_last >= 0 ? s_last + 1 : S;
+    const int kv_end = (kv_len + 63) & ~63;
 
     const int g = lane >> 2, t = lane & 3;
     const int nqb = (S + 15) / 16;
     for (int qb = warp; qb < nqb; qb += kAttnThreads / 32) {
         const int q0 = qb * 16;
-        const int r0 = min(q0 + g, S - 1), r1 = min(q0 + g + 8, S - 1);
+        const int i0 = q0 + g, i1 = q0 + g + 8;
+        h16* out0 = ctx + (static_cast<int64_t>(b) * S + i0) * H + h * kDH + 2 * t;
+        h16* out1 = ctx + (static_cast<int64_t>(b) * S + i1) * H + h * kDH + 2 * t;
+        if (q0 >= kv_len && s_last >= 0) {
+            // query rows past the last real token are never pooled; keep them finite (zeros)
+#pragma unroll
+            for (int db = 0; db < 8; ++db) {
+                if (i0 < S) *reinterpret_cast<uint32_t*>(out0 + db * 8) = 0u;
+                if (i1 < S) *reinterpret_cast<uint32_t*>(out1 + db * 8) = 0u;
+            }
+            continue;
+        }
+        const int r0 = min(i0, S - 1), r1 = min(i1, S - 1);
         // Q fragments straight from global in the m16n8k16 A layout
         uint32_t qa[4][4];
         {
@@ -117,9 +157,10 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
         float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-        const int i0 = q0 + g, i1 = q0 + g + 8;  // unclamped query indices for the bias lookup
+        // bias run of this thread for key block kb: pb[8*n], pb[8*n+1], n = -1..7
+        const float* pb0 = sBias + (OFF - i0 + 2 * t);
 
-        for (int kb = 0; kb < Spad; kb += 64) {
+        for (int kb = 0; kb < kv_end; kb += 64) {
             float s[8][4];
 #pragma unroll
             for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
@@ -136,19 +177,27 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
                     mma_16816<kF16>(s[nb], qa[2 * kp + 1], b2, b3);
                 }
             }
-            // ---- scale + relative-position bias + mask (log2 domain), block row max
+            // ---- scale + relative-position bias (+ mask) in the log2 domain, block row max
+            const float* pb = pb0 + kb;
+            float e0 = pb[-8], e1 = pb[-7];  // bias pair of the previous 8-key group (row g+8)
             float bm0 = -INFINITY, bm1 = -INFINITY;
+            const bool masked_blk = s_blk_clear[kb >> 6] == 0;  // CTA-uniform
 #pragma unroll
             for (int nb = 0; nb < 8; ++nb) {
-                const int j = kb + nb * 8 + 2 * t;
-                const float mk0 = sMask[j], mk1 = sMask[j + 1];
-                // bias index (j - i) + (S-1); clamp only matters for rows/keys outside [0,S)
-                const int ba = min(max(j - i0 + S - 1, 0), 2 * S - 2);
-                const int bb = min(max(j - i1 + S - 1, 0), 2 * S - 2);
-                s[nb][0] = fmaf(s[nb][0], scale_log2e, sBias[ba]) + mk0;
-                s[nb][1] = fmaf(s[nb][1], scale_log2e, sBias[min(ba + 1, 2 * S - 2)]) + mk1;
-                s[nb][2] = fmaf(s[nb][2], scale_log2e, sBias[bb]) + mk0;
-                s[nb][3] = fmaf(s[nb][3], scale_log2e, sBias[min(bb + 1, 2 * S - 2)]) + mk1;
+                const float c0 = pb[nb * 8], c1 = pb[nb * 8 + 1];
+                s[nb][0] = fmaf(s[nb][0], scale_log2e, c0);
+                s[nb][1] = fmaf(s[nb][1], scale_log2e, c1);
+                s[nb][2] = fmaf(s[nb][2], scale_log2e, e0);
+                s[nb][3] = fmaf(s[nb][3], scale_log2e, e1);
+                e0 = c0;
+                e1 = c1;
+                if (masked_blk) {
+                    const float2 mk = *reinterpret_cast<const float2*>(sMask + kb + nb * 8 + 2 * t);
+                    s[nb][0] += mk.x;
+                    s[nb][1] += mk.y;
+                    s[nb][2] += mk.x;
+                    s[nb][3] += mk.y;
+                }
                 bm0 = fmaxf(bm0, fmaxf(s[nb][0], s[nb][1]));
                 bm1 = fmaxf(bm1, fmaxf(s[nb][2], s[nb][3]));
             }
@@ -157,16 +206,16 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
             bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffff, bm1, 1));
             bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffff, bm1, 2));
             const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
-            const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+            const float c0 = fast_exp2(m0 - mn0), c1 = fast_exp2(m1 - mn1);
             m0 = mn0;
             m1 = mn1;
             float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
             for (int nb = 0; nb < 8; ++nb) {
-                s[nb][0] = exp2f(s[nb][0] - mn0);
-                s[nb][1] = exp2f(s[nb][1] - mn0);
-                s[nb][2] = exp2f(s[nb][2] - mn1);
-                s[nb][3] = exp2f(s[nb][3] - mn1);
+                s[nb][0] = fast_exp2(s[nb][0] - mn0);
+                s[nb][1] = fast_exp2(s[nb][1] - mn0);
+                s[nb][2] = fast_exp2(s[nb][2] - mn1);
+                s[nb][3] = fast_exp2(s[nb][3] - mn1);
                 rs0 += s[nb][0] + s[nb][1];
                 rs1 += s[nb][2] + s[nb][3];
             }
@@ -198,14 +247,12 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
                 }
             }
         }
-        // ---- finalise: row sums across the 4 lanes of a quad, normalise, store bf16
+        // ---- finalise: row sums across the 4 lanes of a quad, normalise, store
         l0 += __shfl_xor_sync(0xffffffff, l0, 1);
         l0 += __shfl_xor_sync(0xffffffff, l0, 2);
         l1 += __shfl_xor_sync(0xffffffff, l1, 1);
         l1 += __shfl_xor_sync(0xffffffff, l1, 2);
-        const float inv0 = 1.f / l0, inv1 = 1.f / l1;
-        h16* out0 = ctx + (static_cast<int64_t>(b) * S + i0) * H + h * kDH + 2 * t;
-        h16* out1 = ctx + (static_cast<int64_t>(b) * S + i1) * H + h * kDH + 2 * t;
+        const float inv0 = __fdividef(1.f, l0), inv1 = __fdividef(1.f, l1);
 #pragma unroll
         for (int db = 0; db < 8; ++db) {
             if (i0 < S) *reinterpret_cast<uint32_t*>(out0 + db * 8) = pack16x2<kF16>(o[db][0] * inv0, o[db][1] * inv0);
@@ -218,10 +265,10 @@ int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const i
                      h16* ctx, int B, int S, int heads, int dh, bool fp16, cudaStream_t stream) {
     ARB_REQUIRE(qkv && rel_bias && mask && ctx, "attention: null pointer");
     ARB_REQUIRE(dh == kDH, "attention: head dim %d unsupported (only 64)", dh);
-    ARB_REQUIRE(B > 0 && S > 0 && S <= 768 && S <= max_rel, "attention: bad shape B=%d S=%d max_rel=%d", B, S, max_rel);
+    ARB_REQUIRE(B > 0 && S > 0 && S <= 768 && S <= max_rel && ((S + 63) / 64) <= 16, "attention: bad shape B=%d S=%d max_rel=%d", B, S, max_rel);
     ARB_REQUIRE(B <= 65535, "attention: batch %d exceeds grid.y", B);
     const int Spad = (S + 63) & ~63;
-    const size_t smem = static_cast<size_t>(Spad) * 256 + ((2 * S - 1 + 3) / 4 * 4 + Spad) * sizeof(float);
+    const size_t smem = static_cast<size_t>(Spad) * 256 + (2 * Spad + 32 + Spad) * sizeof(float);
     auto kern = fp16 ? attention_kernel<true> : attention_kernel<false>;
     ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
