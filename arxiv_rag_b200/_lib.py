@@ -83,7 +83,7 @@ SIGNATURES = {
     "arb_gemm16_f32out": (C.c_int, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP]),
     "arb_embed_layernorm": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _F, _I32, _VP]),
     "arb_layernorm16": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _F, _I32, _VP]),
-    "arb_attention16": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "arb_attention16": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "arb_pool_normalize": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP]),
 }
 

@@ -261,8 +261,8 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
     }
 }
 
-int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
-                     h16* ctx, int B, int S, int heads, int dh, bool fp16, cudaStream_t stream) {
+int launch_attention_mma(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
+                         h16* ctx, int B, int S, int heads, int dh, bool fp16, cudaStream_t stream) {
     ARB_REQUIRE(qkv && rel_bias && mask && ctx, "attention: null pointer");
     ARB_REQUIRE(dh == kDH, "attention: head dim %d unsupported (only 64)", dh);
     ARB_REQUIRE(B > 0 && S > 0 && S <= 768 && S <= max_rel && ((S + 63) / 64) <= 16, "attention: bad shape B=%d S=%d max_rel=%d", B, S, max_rel);
@@ -277,6 +277,15 @@ int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const i
                                                          scale_log2e);
     ARB_CHECK_CUDA(cudaGetLastError());
     return ARB_OK;
+}
+
+// impl: 0 = auto (tcgen05 kernel when the shape allows, else mma.sync), 1 = mma.sync, 2 = tcgen05
+int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
+                     h16* ctx, int B, int S, int heads, int dh, bool fp16, int impl, cudaStream_t stream) {
+    ARB_REQUIRE(impl >= 0 && impl <= 2, "attention: impl %d must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)", impl);
+    const bool tc = impl == 2 || (impl == 0 && attention_tc_supported(S, dh));
+    return tc ? launch_attention_tc(qkv, rel_bias, max_rel, mask, ctx, B, S, heads, dh, fp16, stream)
+              : launch_attention_mma(qkv, rel_bias, max_rel, mask, ctx, B, S, heads, dh, fp16, stream);
 }
 
 }  // namespace arb

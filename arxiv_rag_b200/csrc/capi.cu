@@ -164,7 +164,7 @@ static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B
         // q,k,v projections as one [T,H] x [3H,H]^T GEMM (modeling_mpnet.py:145-159)
         if ((rc = launch_gemm16(m->h, H, d.w_qkv, H, m->qkv, 3 * H, d.b_qkv, nullptr, 0, T, 3 * H, H, EPI_BIAS, m->fp16, st))) return rc;
         // softmax(qk^T/8 + position_bias + mask) v (:162-177)
-        if ((rc = launch_attention(m->qkv, m->rel_bias, m->max_seq, mask, m->ctx, B, S, c.num_heads, H / c.num_heads, m->fp16, st))) return rc;
+        if ((rc = launch_attention(m->qkv, m->rel_bias, m->max_seq, mask, m->ctx, B, S, c.num_heads, H / c.num_heads, m->fp16, 0, st))) return rc;
         // o-projection + residual, then post-LN (:183, :210)
         if ((rc = launch_gemm16(m->ctx, H, d.w_o, H, m->tmp, H, d.b_o, m->h, H, T, H, H, EPI_BIAS_RESIDUAL, m->fp16, st))) return rc;
         if ((rc = launch_layernorm(m->tmp, d.ln1_g, d.ln1_b, m->h1, T, H, c.layer_norm_eps, m->fp16, st))) return rc;
@@ -331,11 +331,11 @@ int arb_layernorm16(const void* x, const float* gamma, const float* beta, void* 
 
 int arb_attention16(const void* qkv, const float* rel_bias, int32_t max_rel, const int32_t* mask,
                     void* ctx, int32_t B, int32_t S, int32_t heads, int32_t head_dim, int32_t dtype,
-                    void* stream) {
+                    int32_t impl, void* stream) {
     bool f;
     if (int rc = dtype16(dtype, &f)) return rc;
     return launch_attention(static_cast<const h16*>(qkv), rel_bias, max_rel, mask, static_cast<h16*>(ctx), B, S,
-                            heads, head_dim, f, static_cast<cudaStream_t>(stream));
+                            heads, head_dim, f, impl, static_cast<cudaStream_t>(stream));
 }
 
 int arb_pool_normalize(const void* hidden16, const int32_t* mask, float* out, int32_t B, int32_t S,

@@ -37,7 +37,13 @@ int launch_pool_normalize(const h16* hidden, const int32_t* mask, float* out, in
 // qkv [B*S, 3*H] (q | k | v column blocks), rel_bias fp32 [heads, 2*max_rel-1]
 // (entry r <-> j-i = r-(max_rel-1)), mask int32 [B,S]; ctx [B*S, H].
 int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
-                     h16* ctx, int B, int S, int heads, int dh, bool fp16, cudaStream_t stream);
+                     h16* ctx, int B, int S, int heads, int dh, bool fp16, int impl, cudaStream_t stream);
+// the two implementations behind it: mma.sync flash kernel (any S <= 768) and tcgen05/TMEM kernel
+int launch_attention_mma(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
+                         h16* ctx, int B, int S, int heads, int dh, bool fp16, cudaStream_t stream);
+bool attention_tc_supported(int S, int dh);
+int launch_attention_tc(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
+                        h16* ctx, int B, int S, int heads, int dh, bool fp16, cudaStream_t stream);
 
 // Search: fused score GEMM + per-query running top-k over a bf16 corpus.
 size_t search_workspace_bytes(int64_t Q, int64_t N, int D, int k);

@@ -93,6 +93,16 @@ __device__ __forceinline__ void tma_load_2d(const void* desc, uint64_t* bar, voi
           "r"(c0), "r"(c1), "l"(hint)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(const void* desc, uint64_t* bar, void* smem_dst,
+                                            int32_t c0, int32_t c1, int32_t c2, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)),
+          "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int32_t c0,
                                              int32_t c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -190,6 +200,15 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
                  "r"(r[7])
                  : "memory");
 }
+// 32 lanes x 16 columns store: thread i writes its 16 registers to columns [c, c+16) of lane base+i.
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -214,6 +233,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_16bit(int M, int N, bool fp16) {
     return (1u << 4) | ((fp16 ? 0u : 1u) << 7) | ((fp16 ? 0u : 1u) << 10) |
            (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// Same with B MN-major (bit 16): used for P.V where V is [keys, dh] row-major, i.e. the smem tile
+// rows are K (keys), each row holds the 64 contiguous MN (dh) elements of one 128-byte swizzle
+// row, 8-row groups 1024 B apart — the same SW128 smem descriptor fields as the K-major case.
+__host__ __device__ constexpr uint32_t umma_idesc_16bit_bmn(int M, int N, bool fp16) {
+    return umma_idesc_16bit(M, N, fp16) | (1u << 16);
 }
 
 // ----------------------------------------------------------------------------- misc

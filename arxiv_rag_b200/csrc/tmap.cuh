@@ -44,6 +44,23 @@ inline bool make_tmap_bf16_k64(CUtensorMap* map, const void* base, uint64_t rows
     return r == CUDA_SUCCESS;
 }
 
+// Batched 16-bit matrix [batch, rows, cols] (row stride ld, batch stride rows*ld elements), box =
+// [1, box_rows, 64 cols], 128-byte swizzle. Rows >= `rows` of a batch entry read as zero, so a
+// sequence never sees its neighbour's tokens.
+inline bool make_tmap_bf16_batched_k64(CUtensorMap* map, const void* base, uint64_t batch,
+                                       uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {cols, rows, batch};
+    cuuint64_t strides[2] = {ld * 2, rows * ld * 2};
+    cuuint32_t box[3] = {64, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 // Output / residual tiles: row-major [rows, cols] with `elt_bytes`-wide elements; box =
 // [128 rows, 128 bytes of columns], 128-byte swizzle (the epilogue writes its staging tile with
 // the same XOR pattern). Out-of-bounds rows/columns are clipped on store and zero on load.

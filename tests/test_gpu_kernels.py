@@ -73,8 +73,8 @@ def test_gemm_strided_operands(lib, cuda):
 def test_gemm_rejects_bad_arguments(lib, cuda):
     A = torch.zeros(8, 8, device=cuda, dtype=torch.bfloat16)
     C = torch.zeros(8, 40, device=cuda)
-    assert lib.arb_gemm16_f32out(A.data_ptr(), 8, A.data_ptr(), 8, C.data_ptr(), 40, 8, 40, 8, _lib.ARB_DTYPE_BF16, _stream()) == -1
-    assert b"multiple of 32" in lib.arb_last_error()
+    assert lib.arb_gemm16_f32out(A.data_ptr(), 8, A.data_ptr(), 8, C.data_ptr(), 36, 8, 36, 8, _lib.ARB_DTYPE_BF16, _stream()) == -1
+    assert b"multiple of 8" in lib.arb_last_error()
     assert lib.arb_gemm16_f32out(A.data_ptr(), 8, A.data_ptr(), 8, C.data_ptr(), 32, 8, 32, 8, 9, _stream()) == -1
 
 
@@ -136,15 +136,19 @@ def test_pool_normalize(lib, cuda, dt):
     assert (out[3] == 0).all()
 
 
+@pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("dt", ["bf16", "fp16"])
-@pytest.mark.parametrize("case", [(3, 64, [64, 1, 17]), (4, 100, [100, 37, 0, 99]), (2, 384, [384, 200]), (1, 5, [3])])
-def test_attention(lib, cuda, dt, case):
+@pytest.mark.parametrize("case", [(3, 64, [64, 1, 17]), (4, 100, [100, 37, 0, 99]), (2, 384, [384, 200]), (1, 5, [3]),
+                                  (5, 256, [256, 255, 130, 3, 0]), (3, 200, [200, 101, 100])])
+def test_attention(lib, cuda, dt, case, impl):
     """softmax(qk^T/8 + position_bias + (1-m)*finfo.min) v (modeling_mpnet.py:162-177); S not a
     multiple of the 64-key block, 1-token rows and an all-masked row (uniform attention, as the
     reference's fp32 arithmetic yields)."""
     tdt, code, _ = DT[dt]
     tol = 1.5e-2 if dt == "bf16" else 2e-3
     B, S, lens = case
+    if impl == 2 and S < 64:
+        pytest.skip("tcgen05 attention kernel covers 64 <= S <= 384; shorter sequences use the mma.sync kernel")
     nH, dh, P = 12, 64, 512
     H = nH * dh
     torch.manual_seed(6)
@@ -152,7 +156,7 @@ def test_attention(lib, cuda, dt, case):
     relb = torch.randn(nH, 2 * P - 1, device=cuda) * 0.5
     mask = (torch.arange(S, device=cuda)[None, :] < torch.tensor(lens, device=cuda)[:, None]).int().contiguous()
     ctx = torch.zeros(B * S, H, device=cuda, dtype=tdt)
-    _lib.check(lib.arb_attention16(qkv.data_ptr(), relb.data_ptr(), P, mask.data_ptr(), ctx.data_ptr(), B, S, nH, dh, code, _stream()))
+    _lib.check(lib.arb_attention16(qkv.data_ptr(), relb.data_ptr(), P, mask.data_ptr(), ctx.data_ptr(), B, S, nH, dh, code, impl, _stream()))
     q, k, v = [t.float().view(B, S, nH, dh).transpose(1, 2) for t in qkv.split(H, dim=1)]
     idx = torch.arange(S, device=cuda)
     bias = relb[:, idx[None, :] - idx[:, None] + (P - 1)]

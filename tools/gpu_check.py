@@ -138,8 +138,8 @@ def stage_rowops():
 def stage_attention():
     ok = True
     torch.manual_seed(2)
-    for d in ("bf16", "fp16"):
-        for (B, S, lens) in [(3, 64, [64, 1, 17]), (4, 100, [100, 37, 0, 99]), (2, 384, [384, 200])]:
+    for d, impl in (("bf16", 1), ("fp16", 1), ("bf16", 2), ("fp16", 2)):
+        for (B, S, lens) in [(3, 64, [64, 1, 17]), (4, 100, [100, 37, 0, 99]), (2, 384, [384, 200]), (5, 256, [256, 255, 130, 3, 0])]:
             nH, dh = 12, 64
             H = nH * dh
             P = 512
@@ -148,7 +148,7 @@ def stage_attention():
             mask = (torch.arange(S, device=DEV)[None, :] < torch.tensor(lens, device=DEV)[:, None]).int().contiguous()
             ctx = torch.zeros(B * S, H, device=DEV, dtype=tdtype(d))
             _lib.check(lib().arb_attention16(qkv.data_ptr(), relb.data_ptr(), P, mask.data_ptr(), ctx.data_ptr(), B, S, nH, dh,
-                                             dcode(d), stream()))
+                                             dcode(d), impl, stream()))
             torch.cuda.synchronize()
             q, k, v = [t.float().view(B, S, nH, dh).transpose(1, 2) for t in qkv.split(H, dim=1)]
             idx = torch.arange(S, device=DEV)
@@ -161,7 +161,7 @@ def stage_attention():
             live = ((torch.arange(S, device=DEV)[None, :] < lens_t[:, None]) | (lens_t[:, None] == 0)).reshape(B * S)
             # rows past the last real token are unspecified (finite): compare live rows only
             ok &= bool(torch.isfinite(ctx.float()).all())
-            ok &= report(f"attention {d} B{B} S{S}", ctx[live], ref[live], 1.5e-2 if d == "bf16" else 2e-3)
+            ok &= report(f"attention impl{impl} {d} B{B} S{S}", ctx[live], ref[live], 1.5e-2 if d == "bf16" else 2e-3)
     return ok
 
 
@@ -261,10 +261,11 @@ def stage_perf():
     relb = torch.randn(12, 1023, device=DEV)
     mask = torch.ones(B_, S, device=DEV, dtype=torch.int32)
     ctx = torch.empty(B_ * S, H, device=DEV, dtype=torch.bfloat16)
-    ms = _time(lambda: _lib.check(lib().arb_attention16(qkv.data_ptr(), relb.data_ptr(), 512, mask.data_ptr(), ctx.data_ptr(), B_, S, 12, 64,
-                                                        _lib.ARB_DTYPE_BF16, stream())))
     fl = 4.0 * B_ * 12 * S * S * 64
-    print(f"attention B{B_} S{S}: {ms:.3f} ms {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+    for impl in (1, 2):
+        ms = _time(lambda: _lib.check(lib().arb_attention16(qkv.data_ptr(), relb.data_ptr(), 512, mask.data_ptr(), ctx.data_ptr(), B_, S, 12, 64,
+                                                            _lib.ARB_DTYPE_BF16, impl, stream())))
+        print(f"attention impl{impl} B{B_} S{S}: {ms:.3f} ms {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
     g = torch.ones(H, device=DEV)
     b = torch.zeros(H, device=DEV)
     out = torch.empty_like(ctx)

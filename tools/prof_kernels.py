@@ -42,7 +42,7 @@ for rep in range(2):
         _lib.check(lib.arb_gemm16(A.data_ptr(), K, Ws[(N, K)].data_ptr(), K, C.data_ptr(), N, bias.data_ptr(),
                                   R.data_ptr() if epi == 2 else 0, 768, M, N, K, epi, _lib.ARB_DTYPE_BF16, st()))
     _lib.check(lib.arb_attention16(qkv.data_ptr(), relb.data_ptr(), 512, mask.data_ptr(), ctx.data_ptr(), B, S, 12, 64,
-                                   _lib.ARB_DTYPE_BF16, st()))
+                                   _lib.ARB_DTYPE_BF16, 0, st()))
     for Q in (4096, 64):
         _lib.check(lib.arb_topk_search(queries[Q].data_ptr(), corpus.data_ptr(), 1, Q, N_C, 768, 10, os_.data_ptr(), oi.data_ptr(), 0,
                                        ws.data_ptr(), ws.numel(), st()))
