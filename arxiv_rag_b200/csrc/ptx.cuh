@@ -48,11 +48,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        // suspend-time hint (ns): a waiting role warp sleeps in hardware until the phase flips
+        // instead of re-polling every few cycles and stealing issue slots from the epilogue warps
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, P;\n\t"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x10000u)
         : "memory");
     return ok != 0;
 }

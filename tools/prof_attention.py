@@ -1,0 +1,15 @@
+"""Launch the tcgen05 attention kernel at the bench shape (warm-up + 1 profiled launch)."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from arxiv_rag_b200 import _lib
+lib = _lib.lib()
+B, S, H = int(os.environ.get("PROF_B", 1024)), int(os.environ.get("PROF_S", 384)), 768
+qkv = torch.randn(B * S, 3 * H, device="cuda").to(torch.bfloat16)
+relb = torch.randn(12, 1023, device="cuda")
+mask = torch.ones(B, S, device="cuda", dtype=torch.int32)
+ctx = torch.empty(B * S, H, device="cuda", dtype=torch.bfloat16)
+for _ in range(2):
+    _lib.check(lib.arb_attention16(qkv.data_ptr(), relb.data_ptr(), 512, mask.data_ptr(), ctx.data_ptr(), B, S, 12, 64,
+                                   _lib.ARB_DTYPE_BF16, 2, torch.cuda.current_stream().cuda_stream))
+torch.cuda.synchronize()
+print("ok")
