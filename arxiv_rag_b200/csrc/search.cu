@@ -85,19 +85,36 @@ struct SearchTileIter {
 
 constexpr int kSearchThreads = 192;  // TMA warp, MMA warp, 4 epilogue warps (one per TMEM lane quarter)
 
-// Sorted insert into this thread's shared-memory list (column `row` of the [k][128] arrays);
-// used for k > 16. Strict '<' keeps earlier (smaller-id) entries ahead of equal scores: ids
-// arrive in increasing order.
-__device__ __forceinline__ float list_insert(float* ls, int* li, int k, float v, int id) {
-    int i = k - 1;
-    while (i > 0 && ls[(i - 1) * kBM] < v) {
-        ls[i * kBM] = ls[(i - 1) * kBM];
-        li[i * kBM] = li[(i - 1) * kBM];
-        --i;
+// k > 16: each row's sorted list lives in shared memory ([row][k], row-major) and ONE candidate at
+// a time is inserted by the whole warp: every lane owns list slots lane, lane+32, ... (k <= 128),
+// the insert position is a ballot count of the slots >= v (so equal scores keep arrival = id
+// order), and the tail is shifted down by one slot in parallel. Returns the row's new k-th best.
+__device__ __forceinline__ float warp_list_insert(float* ls, int* li, int k, float v, int id, int lane) {
+    float s[4];
+    int d[4];
+    int pos = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int i = lane + 32 * t;
+        s[t] = i < k ? ls[i] : -INFINITY;
+        d[t] = i < k ? li[i] : -1;
+        pos += __popc(__ballot_sync(0xffffffff, s[t] >= v));
     }
-    ls[i * kBM] = v;
-    li[i * kBM] = id;
-    return ls[(k - 1) * kBM];
+    __syncwarp();  // every slot has been read before any slot is overwritten
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int i = lane + 32 * t;
+        if (i >= pos && i + 1 < k) {
+            ls[i + 1] = s[t];
+            li[i + 1] = d[t];
+        }
+    }
+    if (lane == 0) {
+        ls[pos] = v;
+        li[pos] = id;
+    }
+    __syncwarp();
+    return ls[k - 1];
 }
 
 // Register-resident sorted list (k <= KR <= 16): a branch-free carry chain, 5 instructions per
@@ -144,8 +161,10 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     } else {
         const int lane_grp = warp & 3;
         const int trow = lane_grp * 32 + lane;  // row of the 128-query tile owned by this thread
-        float* ls = reinterpret_cast<float*>(sm.extra()) + trow;                 // [k][128] (KR == 0)
-        int* li = reinterpret_cast<int*>(sm.extra() + static_cast<size_t>(k) * kBM * 4) + trow;
+        float* ls_all = reinterpret_cast<float*>(sm.extra());                    // [128][k] (KR == 0)
+        int* li_all = reinterpret_cast<int*>(sm.extra() + static_cast<size_t>(k) * kBM * 4);
+        float* ls = ls_all + trow * k;
+        int* li = li_all + trow * k;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -163,9 +182,10 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             }
             if (KR == 0) {
                 for (int i = 0; i < k; ++i) {
-                    ls[i * kBM] = -INFINITY;
-                    li[i * kBM] = -1;
+                    ls[i] = -INFINITY;
+                    li[i] = -1;
                 }
+                __syncwarp();  // lists are touched by the whole warp from here on
             }
             float thr = -INFINITY;
             for (int chunk = c_begin; chunk < c_end; ++chunk) {
@@ -194,7 +214,15 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float v = __uint_as_float(r[j]);
-                            if ((full || c0 + j < nvalid) && v > thr) thr = list_insert(ls, li, k, v, id0 + j);
+                            unsigned m = __ballot_sync(0xffffffff, (full || c0 + j < nvalid) && v > thr);
+                            while (m) {  // one candidate (= one row of this warp) at a time, all lanes cooperating
+                                const int src = __ffs(m) - 1;
+                                m &= m - 1;
+                                const float cv = __shfl_sync(0xffffffff, v, src);
+                                const int row = lane_grp * 32 + src;
+                                const float nt = warp_list_insert(ls_all + row * k, li_all + row * k, k, cv, id0 + j, lane);
+                                if (lane == src) thr = nt;
+                            }
                         }
                     }
                 }
@@ -219,8 +247,8 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                         }
                 } else {
                     for (int i = 0; i < k; ++i) {
-                        ps[i] = ls[i * kBM];
-                        pi[i] = li[i * kBM];
+                        ps[i] = ls[i];
+                        pi[i] = li[i];
                     }
                 }
             }

@@ -105,6 +105,8 @@ def cpu_encode_sample(n_target_s: float = 12.0):
     from oracle import encode_oracle as eo
     from oracle import refpath
 
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host core
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     model = refpath.OracleSentenceTransformer(ALL_MPNET_BASE_V2, synthetic_state_dict(ALL_MPNET_BASE_V2, 0))
     ids, mask = eo.synthetic_tokens(64, SEQ, seed=1, full_length=True)
     t0 = time.perf_counter()
