@@ -195,14 +195,18 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                        static_cast<uint32_t>(acc * kSBN);
                 const int64_t n0 = static_cast<int64_t>(chunk) * kSBN;
                 const int nvalid = static_cast<int>(N - n0 < kSBN ? N - n0 : kSBN);
-#pragma unroll 1
-                for (int c0 = 0; c0 < kSBN; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(taddr + c0, r);
-                    tmem_ld_wait();
-                    if (c0 >= nvalid) continue;  // warp-uniform: columns past the corpus end
+                // scan 32 score columns of this thread's query row against its running k-th best
+                auto scan = [&](const uint32_t (&r)[32], int c0) {
+                    if (c0 >= nvalid) return;  // warp-uniform: columns past the corpus end
                     const bool full = c0 + 32 <= nvalid;
                     const int id0 = static_cast<int>(n0) + c0;
+                    // cheap pre-filter: after warm-up almost no 32x32 block holds a survivor
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        mx = fmaxf(mx, (full || c0 + j < nvalid) ? __uint_as_float(r[j]) : -INFINITY);
+                    const float kth = KR > 0 ? rs[KRA - 1] : thr;
+                    if (!__any_sync(0xffffffff, mx > kth)) return;
                     if (KR > 0) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -225,9 +229,20 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                             }
                         }
                     }
+                };
+                // (one instance of the scan code: duplicating it for a second register buffer
+                // overflows the instruction cache and costs more than the TMEM latency it hides)
+#pragma unroll 1
+                for (int c0 = 0; c0 < kSBN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + c0, r);
+                    tmem_ld_wait();
+                    if (c0 + 32 == kSBN) {  // the whole accumulator has been read: hand the TMEM buffer back
+                        tc_fence_before();
+                        mbar_arrive(sm.tmem_empty(acc));
+                    }
+                    scan(r, c0);
                 }
-                tc_fence_before();
-                mbar_arrive(sm.tmem_empty(acc));
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
