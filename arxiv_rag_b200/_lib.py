@@ -81,6 +81,8 @@ SIGNATURES = {
     "arb_topk_search_launches": (C.c_int, [_I32]),
     "arb_gemm16": (C.c_int, [_VP, _I64, _VP, _I64, _VP, _I64, _VP, _VP, _I64, _I64, _I32, _I32, _I32, _I32, _VP]),
     "arb_gemm16_f32out": (C.c_int, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP]),
+    "arb_gemm16_residual_ln": (C.c_int, [_VP, _I64, _VP, _I64, _VP, _I64, _VP, _VP, _I64, _VP, _VP, _F, _I64, _I32, _I32,
+                                         _I32, _VP]),
     "arb_embed_layernorm": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _F, _I32, _VP]),
     "arb_layernorm16": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _F, _I32, _VP]),
     "arb_attention16": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),

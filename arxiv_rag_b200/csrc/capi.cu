@@ -60,6 +60,7 @@ struct Mpnet {
     std::vector<LayerDev> layers;
     h16 *h = nullptr, *h1 = nullptr, *tmp = nullptr, *ctx = nullptr, *qkv = nullptr, *ffn = nullptr;
     bool fp16 = false;
+    bool fuse_ln = false;  // residual GEMMs carry the post-LN in their epilogue (cluster kernel)
 
     template <typename T>
     int alloc(T** p, size_t count) {
@@ -165,13 +166,22 @@ static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B
         if ((rc = launch_gemm16(m->h, H, d.w_qkv, H, m->qkv, 3 * H, d.b_qkv, nullptr, 0, T, 3 * H, H, EPI_BIAS, m->fp16, st))) return rc;
         // softmax(qk^T/8 + position_bias + mask) v (:162-177)
         if ((rc = launch_attention(m->qkv, m->rel_bias, m->max_seq, mask, m->ctx, B, S, c.num_heads, H / c.num_heads, m->fp16, 0, st))) return rc;
-        // o-projection + residual, then post-LN (:183, :210)
-        if ((rc = launch_gemm16(m->ctx, H, d.w_o, H, m->tmp, H, d.b_o, m->h, H, T, H, H, EPI_BIAS_RESIDUAL, m->fp16, st))) return rc;
-        if ((rc = launch_layernorm(m->tmp, d.ln1_g, d.ln1_b, m->h1, T, H, c.layer_norm_eps, m->fp16, st))) return rc;
-        // FFN: GELU(erf) fused in the up-projection epilogue (:225-228), residual in the down (:239-243)
+        // o-projection + residual + post-LN (:183, :210): one cluster kernel when H is a multiple of
+        // 256 (row statistics exchanged through DSMEM), else GEMM then a LayerNorm pass
+        if (m->fuse_ln) {
+            if ((rc = launch_gemm16_ln(m->ctx, H, d.w_o, H, m->h1, H, d.b_o, m->h, H, d.ln1_g, d.ln1_b, c.layer_norm_eps, T, H, H, m->fp16, st))) return rc;
+        } else {
+            if ((rc = launch_gemm16(m->ctx, H, d.w_o, H, m->tmp, H, d.b_o, m->h, H, T, H, H, EPI_BIAS_RESIDUAL, m->fp16, st))) return rc;
+            if ((rc = launch_layernorm(m->tmp, d.ln1_g, d.ln1_b, m->h1, T, H, c.layer_norm_eps, m->fp16, st))) return rc;
+        }
+        // FFN: GELU(erf) fused in the up-projection epilogue (:225-228), residual + post-LN in the down (:239-243)
         if ((rc = launch_gemm16(m->h1, H, d.w_in, H, m->ffn, I, d.b_in, nullptr, 0, T, I, H, EPI_BIAS_GELU, m->fp16, st))) return rc;
-        if ((rc = launch_gemm16(m->ffn, I, d.w_out, I, m->tmp, H, d.b_out, m->h1, H, T, H, I, EPI_BIAS_RESIDUAL, m->fp16, st))) return rc;
-        if ((rc = launch_layernorm(m->tmp, d.ln2_g, d.ln2_b, m->h, T, H, c.layer_norm_eps, m->fp16, st))) return rc;
+        if (m->fuse_ln) {
+            if ((rc = launch_gemm16_ln(m->ffn, I, d.w_out, I, m->h, H, d.b_out, m->h1, H, d.ln2_g, d.ln2_b, c.layer_norm_eps, T, H, I, m->fp16, st))) return rc;
+        } else {
+            if ((rc = launch_gemm16(m->ffn, I, d.w_out, I, m->tmp, H, d.b_out, m->h1, H, T, H, I, EPI_BIAS_RESIDUAL, m->fp16, st))) return rc;
+            if ((rc = launch_layernorm(m->tmp, d.ln2_g, d.ln2_b, m->h, T, H, c.layer_norm_eps, m->fp16, st))) return rc;
+        }
     }
     return launch_pool_normalize(m->h, mask, out, B, S, H, m->fp16, st);
 }
@@ -221,6 +231,13 @@ int arb_mpnet_create(const ArbMpnetConfig* cfg, const ArbMpnetWeights* weights, 
     ARB_REQUIRE(m != nullptr, "mpnet_create: out of host memory");
     m->cfg = *cfg;
     m->fp16 = cfg->compute_dtype == ARB_DTYPE_F16;
+    // The cluster kernel that folds the post-LN into the residual GEMM (gemm16_ln_kernel) is correct
+    // but measured slower than GEMM + LayerNorm pass at the bench shape (1.21 vs 0.46+0.21 ms for
+    // K=768, 2.64 vs 1.43+0.21 ms for K=3072): its per-tile epilogue chain (residual TMA, DSMEM
+    // rendezvous of 3 CTAs, normalise, store) is ~3x the tile's MMA time and only two TMEM
+    // accumulators exist to hide it. It stays available through arb_gemm16_residual_ln; the
+    // encoder keeps the two-kernel path until the chain is shortened.
+    m->fuse_ln = false;
     m->device = device;
     m->max_tokens = max_tokens;
     m->max_seq = max_seq;
@@ -243,7 +260,8 @@ int64_t arb_mpnet_device_bytes(void* handle) { return handle ? static_cast<Mpnet
 
 int arb_mpnet_launches_per_encode(void* handle) {
     if (!handle) return 0;
-    return 2 + 7 * static_cast<Mpnet*>(handle)->cfg.num_layers;
+    const Mpnet* m = static_cast<Mpnet*>(handle);
+    return 2 + (m->fuse_ln ? 5 : 7) * m->cfg.num_layers;
 }
 
 int arb_mpnet_encode(void* handle, const int32_t* ids_dev, const int32_t* mask_dev, int32_t B,
@@ -301,6 +319,17 @@ int arb_gemm16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, 
     return launch_gemm16(static_cast<const h16*>(A), lda, static_cast<const h16*>(B), ldb, static_cast<h16*>(C),
                          ldc, bias, static_cast<const h16*>(R), ldr, M, N, K, epilogue, f,
                          static_cast<cudaStream_t>(stream));
+}
+
+int arb_gemm16_residual_ln(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                           const float* bias, const void* R, int64_t ldr, const float* gamma,
+                           const float* beta, float eps, int64_t M, int32_t N, int32_t K, int32_t dtype,
+                           void* stream) {
+    bool f;
+    if (int rc = dtype16(dtype, &f)) return rc;
+    return launch_gemm16_ln(static_cast<const h16*>(A), lda, static_cast<const h16*>(B), ldb, static_cast<h16*>(C),
+                            ldc, bias, static_cast<const h16*>(R), ldr, gamma, beta, eps, M, N, K, f,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int arb_gemm16_f32out(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,

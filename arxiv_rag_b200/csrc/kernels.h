@@ -19,6 +19,12 @@ enum GemmEpilogue : int {
 int launch_gemm16(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
                   const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
                   int epilogue, bool fp16, cudaStream_t stream);
+// C = LayerNorm(A.B^T + bias + R) * gamma + beta in one kernel (cluster of N/256 CTAs per row block,
+// row statistics exchanged through distributed shared memory). N % 256 == 0, N <= 2048.
+bool gemm16_ln_supported(int N);
+int launch_gemm16_ln(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
+                     const float* bias, const h16* R, int64_t ldr, const float* gamma, const float* beta,
+                     float eps, int64_t M, int N, int K, bool fp16, cudaStream_t stream);
 // Same main loop, fp32 output, no epilogue math (used by the kernel parity tests).
 int launch_gemm16_f32out(const h16* A, int64_t lda, const h16* B, int64_t ldb, float* C,
                          int64_t ldc, int64_t M, int N, int K, bool fp16, cudaStream_t stream);

@@ -132,6 +132,12 @@ int arb_gemm16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, 
                int32_t epilogue, int32_t dtype, void* stream);
 int arb_gemm16_f32out(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
                       int64_t M, int32_t N, int32_t K, int32_t dtype, void* stream);
+/* C = LayerNorm(A . B^T + bias + R) * gamma + beta fused in one kernel (post-LN of
+ * modeling_mpnet.py:210 / :242); N % 256 == 0 and N <= 2048 (a cluster of N/256 CTAs per row block). */
+int arb_gemm16_residual_ln(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                           const float* bias, const void* R, int64_t ldr, const float* gamma,
+                           const float* beta, float eps, int64_t M, int32_t N, int32_t K, int32_t dtype,
+                           void* stream);
 int arb_embed_layernorm(const int32_t* ids, const float* word_emb, const float* pos_emb,
                         const float* gamma, const float* beta, void* out16, int32_t B, int32_t S,
                         int32_t H, int32_t vocab, int32_t max_pos, int32_t pad_id, float eps,

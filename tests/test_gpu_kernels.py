@@ -56,6 +56,29 @@ def test_gemm_epilogues(lib, cuda, dt, epi):
     assert _rel_err(C, ref) < tol
 
 
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+@pytest.mark.parametrize("shape", [(128, 768, 768), (1000, 768, 3072), (333, 256, 128), (5000, 1024, 768)])
+def test_gemm_residual_layernorm_cluster(lib, cuda, dt, shape):
+    """LayerNorm(A.B^T + bias + R) in one kernel: a cluster of N/256 CTAs per row block exchanges
+    the row statistics through distributed shared memory (post-LN of modeling_mpnet.py:210/:242)."""
+    M, N, K = shape
+    tdt, code, _ = DT[dt]
+    torch.manual_seed(7)
+    A = (torch.randn(M, K, device=cuda) * 0.3).to(tdt)
+    B = (torch.randn(N, K, device=cuda) * 0.05).to(tdt)
+    bias = torch.randn(N, device=cuda)
+    R = (torch.randn(M, N, device=cuda) * 2 + 0.3).to(tdt)
+    g = torch.randn(N, device=cuda) * 0.1 + 1
+    b = torch.randn(N, device=cuda) * 0.1
+    C = torch.zeros(M, N, device=cuda, dtype=tdt)
+    _lib.check(lib.arb_gemm16_residual_ln(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, bias.data_ptr(), R.data_ptr(), N,
+                                          g.data_ptr(), b.data_ptr(), 1e-5, M, N, K, code, _stream()))
+    ref = torch.nn.functional.layer_norm(A.float() @ B.float().T + bias + R.float(), (N,), g, b, 1e-5)
+    assert _rel_err(C, ref) < (8e-3 if dt == "bf16" else 1e-3)
+    assert lib.arb_gemm16_residual_ln(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), 96, bias.data_ptr(), R.data_ptr(), N,
+                                      g.data_ptr(), b.data_ptr(), 1e-5, M, 96, K, code, _stream()) == -1  # N % 256 != 0
+
+
 def test_gemm_strided_operands(lib, cuda):
     """The encoder reads q|k|v column blocks and writes into wider buffers: lda/ldc > K/N."""
     torch.manual_seed(2)

@@ -95,6 +95,27 @@ def stage_gemm():
     return ok
 
 
+def stage_gemmln():
+    """Cluster GEMM with fused bias + residual + LayerNorm (DSMEM row statistics)."""
+    ok = True
+    torch.manual_seed(7)
+    for d in ("bf16", "fp16"):
+        for (M, N, K) in [(128, 768, 768), (1000, 768, 3072), (333, 256, 128), (5000, 1024, 768), (70000, 768, 768)]:
+            A = (torch.randn(M, K, device=DEV) * 0.3).to(tdtype(d))
+            B = (torch.randn(N, K, device=DEV) * 0.05).to(tdtype(d))
+            bias = torch.randn(N, device=DEV)
+            R = (torch.randn(M, N, device=DEV) * 2 + 0.3).to(tdtype(d))
+            g = torch.randn(N, device=DEV) * 0.1 + 1
+            b = torch.randn(N, device=DEV) * 0.1
+            C = torch.zeros(M, N, device=DEV, dtype=tdtype(d))
+            _lib.check(lib().arb_gemm16_residual_ln(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, bias.data_ptr(), R.data_ptr(), N,
+                                                    g.data_ptr(), b.data_ptr(), 1e-5, M, N, K, dcode(d), stream()))
+            torch.cuda.synchronize()
+            ref = torch.nn.functional.layer_norm(A.float() @ B.float().T + bias + R.float(), (N,), g, b, 1e-5)
+            ok &= report(f"gemm_residual_ln {d} M{M} N{N} K{K}", C, ref, 8e-3 if d == "bf16" else 1e-3)
+    return ok
+
+
 def stage_rowops():
     ok = True
     torch.manual_seed(1)
@@ -255,6 +276,19 @@ def stage_perf():
         fl = 2.0 * M * N * K
         print(f"gemm M{M} N{N} K{K} epi{epi}: {ms:.3f} ms {fl / ms / 1e9:.1f} TFLOP/s | cuBLAS(no epi) {ms_cublas:.3f} ms {fl / ms_cublas / 1e9:.1f} TFLOP/s", flush=True)
         del A, B, C, R
+    for K in (768, 3072):  # fused bias + residual + LayerNorm cluster GEMM
+        N = 768
+        A = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+        B = (torch.randn(N, K, device=DEV) * 0.05).to(torch.bfloat16)
+        C = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+        R = torch.randn(M, N, device=DEV).to(torch.bfloat16)
+        bias = torch.randn(N, device=DEV)
+        g = torch.ones(N, device=DEV)
+        ms = _time(lambda: _lib.check(lib().arb_gemm16_residual_ln(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, bias.data_ptr(),
+                                                                   R.data_ptr(), N, g.data_ptr(), bias.data_ptr(), 1e-5, M, N, K,
+                                                                   _lib.ARB_DTYPE_BF16, stream())))
+        print(f"gemm+residual+LN fused M{M} N{N} K{K}: {ms:.3f} ms {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
+        del A, B, C, R
     # attention + row ops at the same size
     B_, S, H = 1024, 384, 768
     qkv = torch.randn(B_ * S, 3 * H, device=DEV).to(torch.bfloat16)
@@ -302,7 +336,7 @@ def stage_perf():
     return True
 
 
-STAGES = {"gemm": stage_gemm, "rowops": stage_rowops, "attention": stage_attention, "search": stage_search,
+STAGES = {"gemm": stage_gemm, "gemmln": stage_gemmln, "rowops": stage_rowops, "attention": stage_attention, "search": stage_search,
           "encode": stage_encode, "perf": stage_perf}
 
 if __name__ == "__main__":
