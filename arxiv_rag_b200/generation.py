@@ -55,6 +55,42 @@ def get_worker_model(model_name: str):
     return _worker_model
 
 
+def load_chunks_from_file(file_path, min_quality: float = 0.8) -> List[Dict]:
+    """Chunks of one `{paper_id}.json` whose `metadata.quality_score >= min_quality`
+    (reference :76-92; unreadable files yield [] exactly like the reference)."""
+    import json
+
+    chunks: List[Dict] = []
+    try:
+        with open(file_path, "r", encoding="utf-8") as f:
+            data = json.load(f)
+        for chunk in data.get("chunks", []):
+            if chunk.get("metadata", {}).get("quality_score", 0) >= min_quality:
+                chunks.append(chunk)
+    except Exception:
+        pass
+    return chunks
+
+
+def load_chunks_parallel(output_dir, min_quality: float = 0.8, num_workers: int | None = None) -> List[Dict]:
+    """All high-quality chunks under `output_dir` (reference :94-129: rglob('*.json'), skip '._*').
+
+    Unlike the reference's `Pool.imap_unordered`, files are visited in sorted path order and the
+    result order is deterministic, so row i of the saved matrix means the same chunk on every
+    run. `num_workers` > 1 reads files on a thread pool (JSON decoding
+    releases no GIL, but the I/O overlaps); order is preserved."""
+    from concurrent.futures import ThreadPoolExecutor
+    from pathlib import Path
+
+    files = sorted(f for f in Path(output_dir).rglob("*.json") if not f.name.startswith("._"))
+    if num_workers is None or num_workers <= 1:
+        per_file = [load_chunks_from_file(f, min_quality) for f in files]
+    else:
+        with ThreadPoolExecutor(max_workers=num_workers) as ex:
+            per_file = list(ex.map(lambda f: load_chunks_from_file(f, min_quality), files))
+    return [c for part in per_file for c in part]
+
+
 def generate_embeddings_worker(args: Tuple[Sequence, str, int, int]) -> Tuple[int, List[np.ndarray], Optional[str]]:
     """One task: encode `texts_batch` in sub-batches of `batch_size` (reference :131-177).
 

@@ -112,6 +112,101 @@ def load_embeddings_from_disk(input_dir: str, batch_index: Optional[int] = None)
     return np.vstack(embs), metas
 
 
+class StreamingShardWriter:
+    """Write the batched layout shard by shard while encoding proceeds.
+
+    The reference holds every embedding in RAM until the end and has no resume for the embed
+    stage (generate_embeddings_parallel.py:257, :555). This writer emits exactly the files
+    `save_embeddings_disk` would (`embeddings_batch_{i:04d}.npy` float64, `metadata_batch_{i:04d}.json`,
+    `index.json`), one shard of `batch_size` rows at a time, and rewrites `index.json` atomically
+    (tmp + os.replace, the downloader's idiom at 1-downloader/downloader.py:478-481) after every
+    shard — so `load_embeddings_from_disk` always sees a consistent prefix and an interrupted run
+    resumes at `rows_persisted`. `float32_sidecar=True` also writes `embeddings_f32_batch_XXXX.npy`,
+    the half-size matrix the GPU search stage loads.
+    """
+
+    def __init__(self, output_dir: str, batch_size: int = 10000, float32_sidecar: bool = True):
+        self.out = Path(output_dir)
+        self.out.mkdir(parents=True, exist_ok=True)
+        self.batch_size = int(batch_size)
+        self.sidecar = float32_sidecar
+        self._rows: List[np.ndarray] = []
+        self._chunks: List[Dict] = []
+        self._chunk_ids: List = []
+        self.num_batches = 0
+        self.dim: Optional[int] = None
+        index_file = self.out / "index.json"
+        if index_file.exists():  # resume: trust only what index.json lists
+            with open(index_file, "r", encoding="utf-8") as f:
+                idx = json.load(f)
+            if idx.get("batch_size") != self.batch_size:
+                raise ValueError(f"existing layout has batch_size {idx.get('batch_size')}, not {self.batch_size}")
+            self.num_batches = int(idx["num_batches"])
+            self.dim = idx.get("embedding_dimension")
+            self._chunk_ids = list(idx.get("chunks", []))
+            if len(self._chunk_ids) != self.num_batches * self.batch_size:
+                raise ValueError("existing layout ends with a partial shard; it cannot be extended")
+
+    @property
+    def rows_persisted(self) -> int:
+        """Rows safely on disk (a multiple of batch_size until `close`)."""
+        return len(self._chunk_ids)
+
+    def append(self, chunks: List[Dict], embeddings) -> None:
+        if len(chunks) != len(embeddings):
+            raise ValueError("chunks and embeddings differ in length")
+        for c, e in zip(chunks, embeddings):
+            row = np.asarray(e)
+            if self.dim is None:
+                self.dim = int(row.shape[0])
+            elif row.shape[0] != self.dim:
+                raise ValueError(f"embedding dimension {row.shape[0]} != {self.dim}")
+            self._rows.append(row)
+            self._chunks.append(c)
+            if len(self._rows) == self.batch_size:
+                self._flush()
+
+    def close(self) -> None:
+        if self._rows:
+            self._flush()
+        self._write_index()
+
+    def _flush(self) -> None:
+        i = self.num_batches
+        start = len(self._chunk_ids)
+        arr = _as_matrix(self._rows)
+        np.save(self.out / f"embeddings_batch_{i:04d}.npy", arr)
+        if self.sidecar:
+            np.save(self.out / f"embeddings_f32_batch_{i:04d}.npy", arr.astype(np.float32))
+        metadata = []
+        for j, chunk in enumerate(self._chunks):
+            row = _meta_row(chunk, start + j)
+            row["batch_index"] = i
+            row["batch_position"] = j
+            metadata.append(row)
+        with open(self.out / f"metadata_batch_{i:04d}.json", "w", encoding="utf-8") as f:
+            json.dump(metadata, f, indent=2, ensure_ascii=False)
+        self._chunk_ids.extend(c.get("chunk_id") for c in self._chunks)
+        self.num_batches += 1
+        self._rows, self._chunks = [], []
+        self._write_index()
+
+    def _write_index(self) -> None:
+        index = {
+            "total_embeddings": len(self._chunk_ids),
+            "embedding_dimension": self.dim,
+            "num_batches": self.num_batches,
+            "batch_size": self.batch_size,
+            "chunks": self._chunk_ids,
+        }
+        tmp = self.out / "index.json.tmp"
+        with open(tmp, "w", encoding="utf-8") as f:
+            json.dump(index, f, indent=2)
+        import os
+
+        os.replace(tmp, self.out / "index.json")
+
+
 def save_search_matrix(embeddings, output_dir: str) -> Path:
     """float32 `[N,D]` side file for the GPU search stage (mmap-able, half the float64 bytes)."""
     out = Path(output_dir)
@@ -126,6 +221,13 @@ def load_search_matrix(input_dir: str, mmap: bool = True) -> np.ndarray:
     p = Path(input_dir) / "embeddings_f32.npy"
     if p.exists():
         return np.load(p, mmap_mode="r" if mmap else None)
+    shards = sorted(Path(input_dir).glob("embeddings_f32_batch_*.npy"))
+    index_file = Path(input_dir) / "index.json"
+    if shards and index_file.exists():
+        with open(index_file, "r", encoding="utf-8") as f:
+            n = json.load(f).get("num_batches", 0)
+        if len(shards) >= n > 0:  # shards written by StreamingShardWriter, in index order
+            return np.vstack([np.load(Path(input_dir) / f"embeddings_f32_batch_{i:04d}.npy") for i in range(n)])
     emb, _ = load_embeddings_from_disk(input_dir)
     return np.ascontiguousarray(emb, dtype=np.float32)
 

@@ -118,7 +118,47 @@ def test_batched_layout_round_trip(tmp_path):
     assert np.array_equal(np.asarray(storage.load_search_matrix(str(tmp_path))), rows)
 
 
+def test_streaming_shard_writer_matches_batched_layout_and_resumes(tmp_path):
+    """Shards written while encoding == what save_embeddings_disk writes at the end; an
+    interrupted run leaves a loadable prefix and resumes at rows_persisted."""
+    n = 27
+    rows = np.random.default_rng(1).standard_normal((n, 16)).astype(np.float32)
+    chunks = _chunks(n)
+    ref_dir, out_dir = tmp_path / "ref", tmp_path / "stream"
+    storage.save_embeddings_disk(chunks, list(rows), str(ref_dir), batch_size=10)
+    w = storage.StreamingShardWriter(str(out_dir), batch_size=10)
+    w.append(chunks[:13], list(rows[:13]))  # one full shard flushed, 3 rows pending ... then "crash"
+    assert w.rows_persisted == 10
+    emb, meta = storage.load_embeddings_from_disk(str(out_dir))
+    assert emb.shape == (10, 16) and len(meta) == 10
+    w2 = storage.StreamingShardWriter(str(out_dir), batch_size=10)  # resume
+    assert w2.rows_persisted == 10 and w2.num_batches == 1
+    w2.append(chunks[10:], list(rows[10:]))
+    w2.close()
+    for name in sorted(p.name for p in ref_dir.iterdir()):
+        a, b = (ref_dir / name).read_bytes(), (out_dir / name).read_bytes()
+        assert a == b, f"{name} differs from the reference writer's output"
+    assert np.array_equal(np.asarray(storage.load_search_matrix(str(out_dir))), rows)
+    with pytest.raises(ValueError):
+        storage.StreamingShardWriter(str(out_dir), batch_size=10)  # ends with a partial shard
+
+
 # ------------------------------------------------------------------ task split / sharding
+def test_chunk_ingest_quality_filter_and_order(tmp_path):
+    """load_chunks_* (reference :76-129): quality filter, '._' files skipped, broken files
+    ignored, deterministic order (the reference's imap_unordered is not)."""
+    for p, qs in (("b/2.json", [0.95, 0.5]), ("a/1.json", [0.9, 0.85, 0.99]), ("a/._1.json", [1.0])):
+        f = tmp_path / p
+        f.parent.mkdir(exist_ok=True)
+        f.write_text(json.dumps({"chunks": [{"chunk_id": f"{p}:{i}", "text": "t", "metadata": {"quality_score": q}}
+                                            for i, q in enumerate(qs)]}))
+    (tmp_path / "a" / "broken.json").write_text("{not json")
+    got = generation.load_chunks_parallel(tmp_path, min_quality=0.9)
+    assert [c["chunk_id"] for c in got] == ["a/1.json:0", "a/1.json:2", "b/2.json:0"]
+    assert generation.load_chunks_parallel(tmp_path, min_quality=0.9, num_workers=4) == got
+    assert len(generation.load_chunks_from_file(tmp_path / "a" / "1.json")) == 3  # default 0.8
+
+
 def test_task_split_and_reorder():
     tasks = generation.split_tasks(1234, 500)
     assert tasks == [(0, 0, 500), (1, 500, 1000), (2, 1000, 1234)]
