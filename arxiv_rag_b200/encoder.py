@@ -119,6 +119,33 @@ class B200SentenceEncoder:
                                                _lib.ptr(out), _lib.current_stream()))
         return out
 
+    def encode_tokens_graphed(self, ids_dev, mask_dev):
+        """Same as `encode_tokens` through a CUDA graph cached per (B, S): the 86 launches of a
+        forward become one graph launch, which is what bounds small-batch (query-time) latency.
+        Inputs are copied into the graph's static buffers; the returned tensor is the graph's
+        static output (valid until the next call with the same shape)."""
+        torch = self._torch
+        B, S = ids_dev.shape
+        key = (B, S)
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        if key not in self._graphs:
+            s_ids, s_mask = torch.empty_like(ids_dev), torch.empty_like(mask_dev)
+            s_out = torch.empty((B, self.arch.hidden_size), dtype=torch.float32, device=ids_dev.device)
+            s_ids.copy_(ids_dev)
+            s_mask.copy_(mask_dev)
+            self.encode_tokens(s_ids, s_mask, s_out)  # warm-up outside capture (module load, attributes)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.encode_tokens(s_ids, s_mask, s_out)
+            self._graphs[key] = (graph, s_ids, s_mask, s_out)
+        graph, s_ids, s_mask, s_out = self._graphs[key]
+        s_ids.copy_(ids_dev, non_blocking=True)
+        s_mask.copy_(mask_dev, non_blocking=True)
+        graph.replay()
+        return s_out
+
     @property
     def launches_per_encode(self) -> int:
         return int(_lib.lib().arb_mpnet_launches_per_encode(self._h))

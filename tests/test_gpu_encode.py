@@ -129,6 +129,23 @@ def test_batching_and_order_invariance(cuda, full_model):
     enc.close()
 
 
+def test_cuda_graph_path_is_identical(cuda, full_model):
+    """encode_tokens_graphed replays the same kernels from a CUDA graph: bit-identical output,
+    also when the graph is reused with new inputs of the same shape."""
+    import torch
+
+    arch, sd, _ = full_model
+    enc = _encoder(arch, sd, "bf16", max_batch=8, max_seq=64)
+    for seed in (41, 42):
+        ids, mask = eo.synthetic_tokens(8, 64, seed=seed)
+        d_ids, d_mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+        a = enc.encode_tokens(d_ids, d_mask).clone()
+        b = enc.encode_tokens_graphed(d_ids, d_mask).clone()
+        assert torch.equal(a, b)
+    assert len(enc._graphs) == 1
+    enc.close()
+
+
 def test_reference_worker_api(cuda, full_model):
     """generate_embeddings_worker / generate_embeddings_parallel (reference :131-269): tuple shape,
     row type, order; compared with the oracle's restatement of the same control flow."""
