@@ -40,6 +40,7 @@ class MpnetConfig(C.Structure):
         ("pad_token_id", C.c_int32),
         ("layer_norm_eps", C.c_float),
         ("compute_dtype", C.c_int32),
+        ("position_mode", C.c_int32),
     ]
 
 
@@ -79,11 +80,12 @@ SIGNATURES = {
     "arb_topk_search": (C.c_int, [_VP, _VP, _I32, _I64, _I64, _I32, _I32, _VP, _VP, _I64, _VP, _SZ, _VP]),
     "arb_topk_merge": (C.c_int, [_VP, _VP, _I32, _I64, _I32, _VP, _VP, _VP]),
     "arb_topk_search_launches": (C.c_int, [_I32]),
+    "arb_adjacent_cosine": (C.c_int, [_VP, _I64, _I32, _VP, _VP]),
     "arb_gemm16": (C.c_int, [_VP, _I64, _VP, _I64, _VP, _I64, _VP, _VP, _I64, _I64, _I32, _I32, _I32, _I32, _VP]),
     "arb_gemm16_f32out": (C.c_int, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP]),
     "arb_gemm16_residual_ln": (C.c_int, [_VP, _I64, _VP, _I64, _VP, _I64, _VP, _VP, _I64, _VP, _VP, _F, _I64, _I32, _I32,
                                          _I32, _VP]),
-    "arb_embed_layernorm": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _F, _I32, _VP]),
+    "arb_embed_layernorm": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F, _I32, _VP]),
     "arb_layernorm16": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _F, _I32, _VP]),
     "arb_attention16": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "arb_pool_normalize": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP]),

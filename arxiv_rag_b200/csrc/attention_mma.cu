@@ -1,16 +1,19 @@
-// Fused self-attention for the MPNet encoder: softmax(q.k^T/sqrt(dh) + rel_bias + mask) . v
+// Fused self-attention, mma.sync version: softmax(q.k^T/sqrt(dh) + rel_bias + mask) . v
 // per (sequence, head), never materialising the [S,S] probability matrix in HBM.
 // Follows MPNetSelfAttention.forward (modeling_mpnet.py:162-177) with the shared relative
 // position bias of MPNetEncoder.compute_position_bias (:324-360) and the additive mask
-// (1-m)*finfo.min of get_extended_attention_mask (modeling_utils.py:936-947).
+// (1-m)*finfo.min of get_extended_attention_mask (modeling_utils.py:936-947). With a NULL bias
+// table it is BertSelfAttention (the all-MiniLM-L6-v2 encoder of the second encode call site,
+// 3-chunks/pipeline/src/processors/text_processor.py:1379-1396). Head dim 64 or 32.
 //
-// One CTA per (sequence, head): K and V of the head ([S,64] 16-bit each) are staged once in
+// One CTA per (sequence, head): K and V of the head ([S,dh] 16-bit each) are staged once in
 // shared memory (XOR-swizzled 16-byte chunks, conflict-free for ldmatrix); each warp then
 // runs a flash-style online softmax over 16-query-row blocks with mma.sync tiles and fp32
 // statistics/accumulators. The relative-position bias depends only on j-i, so a thread reads it
 // as one contiguous run of a padded table (rows g and g+8 share the run shifted by 8 keys).
 // Keys after the last unmasked key contribute exactly 0 in the reference's fp32 arithmetic, so
 // key blocks beyond it are skipped (unless the whole row is masked: uniform attention).
+// The encode path uses the tcgen05 kernel (attention_tc.cu) when 64 <= S <= 384 and dh == 64.
 #include "common.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -18,7 +21,6 @@
 namespace arb {
 
 constexpr int kAttnThreads = 256;
-constexpr int kDH = 64;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kMaskMin = -3.4028234663852886e38f;  // torch.finfo(float32).min
 
@@ -60,24 +62,36 @@ __device__ __forceinline__ float fast_exp2(float x) {  // single MUFU.EX2; exp2(
     return y;
 }
 
-template <bool kF16>
+// byte offset of 16-byte chunk c of key row r: rows are DH*2 bytes; the XOR keeps the 8 rows an
+// ldmatrix touches on 8 different bank groups (128-byte rows: r&7; 64-byte rows: (r>>1)&3)
+template <int DH>
+__device__ __forceinline__ uint32_t kv_off(int r, int c) {
+    if constexpr (DH == 64) return r * 128 + ((c ^ (r & 7)) << 4);
+    else return r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+}
+
+template <bool kF16, int DH>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias, int max_rel,
                  const int32_t* __restrict__ mask, h16* __restrict__ ctx, int S, int heads,
                  float scale_log2e) {
+    constexpr int CPR = DH / 8;    // 16-byte chunks per row
+    constexpr int KS = DH / 16;    // k-steps of q.k^T
+    constexpr int DB = DH / 8;     // 8-wide output dim blocks
+    constexpr int RB = DH * 2;     // row bytes
     extern __shared__ __align__(128) uint8_t smem_attn[];
     const int Spad = (S + 63) & ~63;
     const int OFF = Spad + 16;                                // bias table: entry (j - i) + OFF
     const int nbias = 2 * Spad + 32;
-    uint8_t* sK = smem_attn;                                  // [Spad][128 B], swizzled
-    uint8_t* sV = sK + static_cast<size_t>(Spad) * 128;       // [Spad][128 B], swizzled
-    float* sBias = reinterpret_cast<float*>(sV + static_cast<size_t>(Spad) * 128);  // [nbias], x log2e
+    uint8_t* sK = smem_attn;                                  // [Spad][RB], swizzled
+    uint8_t* sV = sK + static_cast<size_t>(Spad) * RB;        // [Spad][RB], swizzled
+    float* sBias = reinterpret_cast<float*>(sV + static_cast<size_t>(Spad) * RB);  // [nbias], x log2e
     float* sMask = sBias + nbias;                             // [Spad] additive, log2 domain
     __shared__ int s_last;                                    // index of the last unmasked key, -1 if none
     __shared__ int s_blk_clear[16];                           // per 64-key block: 1 = no masked / out-of-range key
 
     const int h = blockIdx.x, b = blockIdx.y;
-    const int H = heads * kDH;
+    const int H = heads * DH;
     const int64_t ld = 3 * static_cast<int64_t>(H);
     const h16* base = qkv + static_cast<int64_t>(b) * S * ld;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -86,20 +100,19 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
     if (tid == 0) s_last = -1;
     if (tid < 16) s_blk_clear[tid] = 1;
     const uint32_t sK_u = smem_u32(sK), sV_u = smem_u32(sV);
-    for (int idx = tid; idx < Spad * 16; idx += kAttnThreads) {
-        const int r = idx >> 4, c = idx & 7, isv = (idx >> 3) & 1;
-        const uint32_t dst = (isv ? sV_u : sK_u) + r * 128 + ((c ^ (r & 7)) << 4);
+    for (int idx = tid; idx < Spad * 2 * CPR; idx += kAttnThreads) {
+        const int r = idx / (2 * CPR), w = idx % (2 * CPR), c = w % CPR, isv = w / CPR;
+        const uint32_t off = kv_off<DH>(r, c);
         if (r < S) {
-            cp_async16(dst, base + static_cast<int64_t>(r) * ld + (isv ? 2 * H : H) + h * kDH + c * 8);
+            cp_async16((isv ? sV_u : sK_u) + off, base + static_cast<int64_t>(r) * ld + (isv ? 2 * H : H) + h * DH + c * 8);
         } else {
-            *reinterpret_cast<uint4*>((isv ? sV : sK) + r * 128 + ((c ^ (r & 7)) << 4)) =
-                make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>((isv ? sV : sK) + off) = make_uint4(0, 0, 0, 0);
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     for (int i = tid; i < nbias; i += kAttnThreads) {
         const int rel = i - OFF;  // j - i_query
-        sBias[i] = (rel > -S && rel < S)
+        sBias[i] = (rel_bias != nullptr && rel > -S && rel < S)
                        ? rel_bias[static_cast<int64_t>(h) * (2 * max_rel - 1) + rel + (max_rel - 1)] * kLog2e
                        : 0.f;
     }
@@ -128,12 +141,12 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
     for (int qb = warp; qb < nqb; qb += kAttnThreads / 32) {
         const int q0 = qb * 16;
         const int i0 = q0 + g, i1 = q0 + g + 8;
-        h16* out0 = ctx + (static_cast<int64_t>(b) * S + i0) * H + h * kDH + 2 * t;
-        h16* out1 = ctx + (static_cast<int64_t>(b) * S + i1) * H + h * kDH + 2 * t;
+        h16* out0 = ctx + (static_cast<int64_t>(b) * S + i0) * H + h * DH + 2 * t;
+        h16* out1 = ctx + (static_cast<int64_t>(b) * S + i1) * H + h * DH + 2 * t;
         if (q0 >= kv_len && s_last >= 0) {
             // query rows past the last real token are never pooled; keep them finite (zeros)
 #pragma unroll
-            for (int db = 0; db < 8; ++db) {
+            for (int db = 0; db < DB; ++db) {
                 if (i0 < S) *reinterpret_cast<uint32_t*>(out0 + db * 8) = 0u;
                 if (i1 < S) *reinterpret_cast<uint32_t*>(out1 + db * 8) = 0u;
             }
@@ -141,21 +154,21 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
         }
         const int r0 = min(i0, S - 1), r1 = min(i1, S - 1);
         // Q fragments straight from global in the m16n8k16 A layout
-        uint32_t qa[4][4];
+        uint32_t qa[KS][4];
         {
-            const h16* q_r0 = base + static_cast<int64_t>(r0) * ld + h * kDH;
-            const h16* q_r1 = base + static_cast<int64_t>(r1) * ld + h * kDH;
+            const h16* q_r0 = base + static_cast<int64_t>(r0) * ld + h * DH;
+            const h16* q_r1 = base + static_cast<int64_t>(r1) * ld + h * DH;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
+            for (int ks = 0; ks < KS; ++ks) {
                 qa[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(q_r0 + ks * 16 + 2 * t));
                 qa[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(q_r1 + ks * 16 + 2 * t));
                 qa[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(q_r0 + ks * 16 + 8 + 2 * t));
                 qa[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(q_r1 + ks * 16 + 8 + 2 * t));
             }
         }
-        float o[8][4];
+        float o[DB][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+        for (int i = 0; i < DB; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
         float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
         // bias run of this thread for key block kb: pb[8*n], pb[8*n+1], n = -1..7
         const float* pb0 = sBias + (OFF - i0 + 2 * t);
@@ -169,10 +182,10 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
             for (int nb = 0; nb < 8; ++nb) {
                 const int key = kb + nb * 8 + (lane & 7);
 #pragma unroll
-                for (int kp = 0; kp < 2; ++kp) {
+                for (int kp = 0; kp < KS / 2; ++kp) {
                     uint32_t b0, b1, b2, b3;
                     const int chunk = 4 * kp + (lane >> 3);
-                    ldmatrix_x4(sK_u + key * 128 + ((chunk ^ (key & 7)) << 4), b0, b1, b2, b3);
+                    ldmatrix_x4(sK_u + kv_off<DH>(key, chunk), b0, b1, b2, b3);
                     mma_16816<kF16>(s[nb], qa[2 * kp], b0, b1);
                     mma_16816<kF16>(s[nb], qa[2 * kp + 1], b2, b3);
                 }
@@ -222,7 +235,7 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
             l0 = l0 * c0 + rs0;
             l1 = l1 * c1 + rs1;
 #pragma unroll
-            for (int db = 0; db < 8; ++db) {
+            for (int db = 0; db < DB; ++db) {
                 o[db][0] *= c0;
                 o[db][1] *= c0;
                 o[db][2] *= c1;
@@ -238,10 +251,10 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
                 pa[3] = pack16x2<kF16>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
                 const int key = kb + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
 #pragma unroll
-                for (int dp = 0; dp < 4; ++dp) {
+                for (int dp = 0; dp < DB / 2; ++dp) {
                     uint32_t b0, b1, b2, b3;
                     const int chunk = 2 * dp + (lane >> 4);
-                    ldmatrix_x4_trans(sV_u + key * 128 + ((chunk ^ (key & 7)) << 4), b0, b1, b2, b3);
+                    ldmatrix_x4_trans(sV_u + kv_off<DH>(key, chunk), b0, b1, b2, b3);
                     mma_16816<kF16>(o[2 * dp], pa, b0, b1);
                     mma_16816<kF16>(o[2 * dp + 1], pa, b2, b3);
                 }
@@ -254,7 +267,7 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
         l1 += __shfl_xor_sync(0xffffffff, l1, 2);
         const float inv0 = __fdividef(1.f, l0), inv1 = __fdividef(1.f, l1);
 #pragma unroll
-        for (int db = 0; db < 8; ++db) {
+        for (int db = 0; db < DB; ++db) {
             if (i0 < S) *reinterpret_cast<uint32_t*>(out0 + db * 8) = pack16x2<kF16>(o[db][0] * inv0, o[db][1] * inv0);
             if (i1 < S) *reinterpret_cast<uint32_t*>(out1 + db * 8) = pack16x2<kF16>(o[db][2] * inv1, o[db][3] * inv1);
         }
@@ -263,13 +276,16 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
 
 int launch_attention_mma(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
                          h16* ctx, int B, int S, int heads, int dh, bool fp16, cudaStream_t stream) {
-    ARB_REQUIRE(qkv && rel_bias && mask && ctx, "attention: null pointer");
-    ARB_REQUIRE(dh == kDH, "attention: head dim %d unsupported (only 64)", dh);
-    ARB_REQUIRE(B > 0 && S > 0 && S <= 768 && S <= max_rel && ((S + 63) / 64) <= 16, "attention: bad shape B=%d S=%d max_rel=%d", B, S, max_rel);
+    ARB_REQUIRE(qkv && mask && ctx, "attention: null pointer");
+    ARB_REQUIRE(dh == 64 || dh == 32, "attention: head dim %d unsupported (64 or 32)", dh);
+    ARB_REQUIRE(B > 0 && S > 0 && S <= 768 && (rel_bias == nullptr || S <= max_rel) && ((S + 63) / 64) <= 16,
+                "attention: bad shape B=%d S=%d max_rel=%d", B, S, max_rel);
     ARB_REQUIRE(B <= 65535, "attention: batch %d exceeds grid.y", B);
     const int Spad = (S + 63) & ~63;
-    const size_t smem = static_cast<size_t>(Spad) * 256 + (2 * Spad + 32 + Spad) * sizeof(float);
-    auto kern = fp16 ? attention_kernel<true> : attention_kernel<false>;
+    const size_t smem = static_cast<size_t>(Spad) * 4 * dh + (2 * Spad + 32 + Spad) * sizeof(float);
+    void (*kern)(const h16*, const float*, int, const int32_t*, h16*, int, int, float);
+    if (dh == 64) kern = fp16 ? attention_kernel<true, 64> : attention_kernel<false, 64>;
+    else kern = fp16 ? attention_kernel<true, 32> : attention_kernel<false, 32>;
     ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
     const float scale_log2e = kLog2e / sqrtf(static_cast<float>(dh));
@@ -283,7 +299,7 @@ int launch_attention_mma(const h16* qkv, const float* rel_bias, int max_rel, con
 int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
                      h16* ctx, int B, int S, int heads, int dh, bool fp16, int impl, cudaStream_t stream) {
     ARB_REQUIRE(impl >= 0 && impl <= 2, "attention: impl %d must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)", impl);
-    const bool tc = impl == 2 || (impl == 0 && attention_tc_supported(S, dh));
+    const bool tc = impl == 2 || (impl == 0 && rel_bias != nullptr && attention_tc_supported(S, dh));
     return tc ? launch_attention_tc(qkv, rel_bias, max_rel, mask, ctx, B, S, heads, dh, fp16, stream)
               : launch_attention_mma(qkv, rel_bias, max_rel, mask, ctx, B, S, heads, dh, fp16, stream);
 }

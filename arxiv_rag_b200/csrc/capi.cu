@@ -102,7 +102,8 @@ static int mpnet_build(Mpnet* m, const ArbMpnetWeights* w) {
     if (int rc = m->upload_f32(&m->emb_g, w->emb_ln_g, H)) return rc;
     if (int rc = m->upload_f32(&m->emb_b, w->emb_ln_b, H)) return rc;
     // expand the bucketed relative bias once: it depends only on j-i (modeling_mpnet.py:324-341)
-    {
+    // (a BERT-style encoder has none: relative_attention_num_buckets == 0 -> attention without bias)
+    if (c.relative_attention_num_buckets > 0) {
         ARB_REQUIRE(w->relative_attention_bias != nullptr, "mpnet_create: missing relative_attention_bias");
         const int P = m->max_seq, W = 2 * P - 1;
         std::vector<float> tbl(static_cast<size_t>(c.num_heads) * W);
@@ -157,7 +158,7 @@ static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B
     const int64_t T = static_cast<int64_t>(B) * S;
     int rc;
     if ((rc = launch_embed_ln(ids, m->word_emb, m->pos_emb, m->emb_g, m->emb_b, m->h, B, S, H,
-                              c.vocab_size, c.max_position_embeddings, c.pad_token_id,
+                              c.vocab_size, c.max_position_embeddings, c.pad_token_id, c.position_mode,
                               c.layer_norm_eps, m->fp16, st)))
         return rc;
     for (int l = 0; l < c.num_layers; ++l) {
@@ -205,8 +206,10 @@ int arb_mpnet_create(const ArbMpnetConfig* cfg, const ArbMpnetWeights* weights, 
     ARB_REQUIRE(weights->layers != nullptr, "mpnet_create: null layer array");
     ARB_REQUIRE(cfg->hidden_size > 0 && cfg->num_heads > 0 && cfg->hidden_size % cfg->num_heads == 0,
                 "mpnet_create: bad hidden/heads %d/%d", cfg->hidden_size, cfg->num_heads);
-    ARB_REQUIRE(cfg->hidden_size / cfg->num_heads == 64, "mpnet_create: head dim %d unsupported (64 only)",
-                cfg->hidden_size / cfg->num_heads);
+    ARB_REQUIRE(cfg->hidden_size / cfg->num_heads == 64 || cfg->hidden_size / cfg->num_heads == 32,
+                "mpnet_create: head dim %d unsupported (64 or 32)", cfg->hidden_size / cfg->num_heads);
+    ARB_REQUIRE(cfg->position_mode == 0 || cfg->position_mode == 1, "mpnet_create: position_mode %d must be 0 or 1",
+                cfg->position_mode);
     ARB_REQUIRE(cfg->hidden_size % 128 == 0 && cfg->hidden_size <= 1024, "mpnet_create: hidden size %d unsupported", cfg->hidden_size);
     ARB_REQUIRE(cfg->intermediate_size % 32 == 0, "mpnet_create: intermediate size %d unsupported", cfg->intermediate_size);
     ARB_REQUIRE(cfg->compute_dtype == ARB_DTYPE_BF16 || cfg->compute_dtype == ARB_DTYPE_F16,
@@ -215,7 +218,7 @@ int arb_mpnet_create(const ArbMpnetConfig* cfg, const ArbMpnetWeights* weights, 
                 "mpnet_create: bad layer/vocab/position counts");
     ARB_REQUIRE(max_tokens > 0 && max_seq > 0 && max_seq <= 768, "mpnet_create: bad max_tokens=%lld / max_seq=%d",
                 (long long)max_tokens, max_seq);
-    ARB_REQUIRE(max_seq + cfg->pad_token_id < cfg->max_position_embeddings,
+    ARB_REQUIRE((cfg->position_mode == 1 ? max_seq - 1 : max_seq + cfg->pad_token_id) < cfg->max_position_embeddings,
                 "mpnet_create: max_seq %d exceeds the position table (%d rows)", max_seq, cfg->max_position_embeddings);
     int ndev = 0;
     ARB_CHECK_CUDA(cudaGetDeviceCount(&ndev));
@@ -342,12 +345,17 @@ int arb_gemm16_f32out(const void* A, int64_t lda, const void* B, int64_t ldb, fl
 
 int arb_embed_layernorm(const int32_t* ids, const float* word_emb, const float* pos_emb,
                         const float* gamma, const float* beta, void* out16, int32_t B, int32_t S,
-                        int32_t H, int32_t vocab, int32_t max_pos, int32_t pad_id, float eps,
-                        int32_t dtype, void* stream) {
+                        int32_t H, int32_t vocab, int32_t max_pos, int32_t pad_id, int32_t position_mode,
+                        float eps, int32_t dtype, void* stream) {
     bool f;
     if (int rc = dtype16(dtype, &f)) return rc;
+    ARB_REQUIRE(position_mode == 0 || position_mode == 1, "embed_layernorm: position_mode %d must be 0 or 1", position_mode);
     return launch_embed_ln(ids, word_emb, pos_emb, gamma, beta, static_cast<h16*>(out16), B, S, H, vocab,
-                           max_pos, pad_id, eps, f, static_cast<cudaStream_t>(stream));
+                           max_pos, pad_id, position_mode, eps, f, static_cast<cudaStream_t>(stream));
+}
+
+int arb_adjacent_cosine(const float* emb_dev, int64_t n, int32_t D, float* out_dev, void* stream) {
+    return launch_adjacent_cosine(emb_dev, out_dev, n, D, static_cast<cudaStream_t>(stream));
 }
 
 int arb_layernorm16(const void* x, const float* gamma, const float* beta, void* out, int64_t rows,

@@ -32,13 +32,16 @@ int launch_gemm16_f32out(const h16* A, int64_t lda, const h16* B, int64_t ldb, f
 // word_emb[ids] + pos_emb[position_ids(ids)] -> LayerNorm -> 16-bit hidden [B*S, H]
 int launch_embed_ln(const int32_t* ids, const float* word_emb, const float* pos_emb,
                     const float* gamma, const float* beta, h16* out, int B, int S, int H, int vocab,
-                    int max_pos, int pad_id, float eps, bool fp16, cudaStream_t stream);
+                    int max_pos, int pad_id, int pos_mode /* 0 MPNet pad-aware, 1 absolute */, float eps, bool fp16,
+                    cudaStream_t stream);
 // out = LayerNorm(x) row-wise, x 16-bit [rows, H] (already holds GEMM output + residual).
 int launch_layernorm(const h16* x, const float* gamma, const float* beta, h16* out, int64_t rows,
                      int H, float eps, bool fp16, cudaStream_t stream);
 // masked mean over tokens then L2 normalise: hidden [B,S,H], mask int32 [B,S] -> fp32 [B,H]
 int launch_pool_normalize(const h16* hidden, const int32_t* mask, float* out, int B, int S, int H,
                           bool fp16, cudaStream_t stream);
+// out[i] = cos(emb[i], emb[i-1]) (out[0] = 1): the adjacent-sentence similarity of semantic chunking
+int launch_adjacent_cosine(const float* emb, float* out, int64_t n, int D, cudaStream_t stream);
 // softmax(q.k^T/sqrt(dh) + rel_bias[h][j-i] + mask) . v for every (batch, head);
 // qkv [B*S, 3*H] (q | k | v column blocks), rel_bias fp32 [heads, 2*max_rel-1]
 // (entry r <-> j-i = r-(max_rel-1)), mask int32 [B,S]; ctx [B*S, H].

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256)
 embed_ln_kernel(const int32_t* __restrict__ ids, const float* __restrict__ word_emb,
                 const float* __restrict__ pos_emb, const float* __restrict__ gamma,
                 const float* __restrict__ beta, h16* __restrict__ out, int S, int H,
-                int vocab, int max_pos, int pad_id, float eps) {
+                int vocab, int max_pos, int pad_id, int pos_mode, float eps) {
     extern __shared__ int smem_i[];
     int* s_pos = smem_i;              // [S] position id of each token
     int* s_chunk = smem_i + S;        // [ceil(S/32)] non-pad count per 32-token chunk
@@ -82,6 +82,7 @@ embed_ln_kernel(const int32_t* __restrict__ ids, const float* __restrict__ word_
             for (int j = 0; j < c; ++j) p += s_chunk[j];
             p += pad_id;
         }
+        if (pos_mode == 1) p = s;  // BERT: absolute position = token index (BertEmbeddings.position_ids)
         s_pos[s] = min(p, max_pos - 1);
     }
     __syncthreads();
@@ -192,6 +193,44 @@ pool_normalize_kernel(const h16* __restrict__ hidden, const int32_t* __restrict_
     }
 }
 
+// cos(e[i], e[i-1]) for consecutive rows — TextChunker._cosine_similarity
+// (text_processor.py:1601-1605) over the adjacent sentence pairs of _chunk_semantic (:1547-1561).
+// One warp per row; out[0] = 1.
+__global__ void __launch_bounds__(256)
+adjacent_cosine_kernel(const float* __restrict__ emb, float* __restrict__ out, int64_t n, int D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    if (i == 0) {
+        if (lane == 0) out[0] = 1.0f;
+        return;
+    }
+    const float* a = emb + i * D;
+    const float* b = a - D;
+    float dot = 0.f, na = 0.f, nb = 0.f;
+    for (int d = lane * 4; d < D; d += 128) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(a + d));
+        const float4 y = __ldg(reinterpret_cast<const float4*>(b + d));
+        dot += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+        na += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        nb += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+    }
+    dot = warp_sum(dot);
+    na = warp_sum(na);
+    nb = warp_sum(nb);
+    if (lane == 0) out[i] = dot / (sqrtf(na) * sqrtf(nb));
+}
+
+int launch_adjacent_cosine(const float* emb, float* out, int64_t n, int D, cudaStream_t stream) {
+    ARB_REQUIRE(emb && out, "adjacent_cosine: null pointer");
+    ARB_REQUIRE(n > 0 && D > 0 && D % 4 == 0, "adjacent_cosine: bad shape n=%lld D=%d", (long long)n, D);
+    const int64_t blocks = (n + 7) / 8;
+    ARB_REQUIRE(blocks < (1ll << 31), "adjacent_cosine: n too large");
+    adjacent_cosine_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(emb, out, n, D);
+    ARB_CHECK_CUDA(cudaGetLastError());
+    return ARB_OK;
+}
+
 static int check_h(int H) {
     ARB_REQUIRE(H > 0 && H % 128 == 0 && H <= 128 * kMaxVec, "hidden size %d unsupported (need H %% 128 == 0, H <= %d)", H, 128 * kMaxVec);
     return ARB_OK;
@@ -199,14 +238,14 @@ static int check_h(int H) {
 
 int launch_embed_ln(const int32_t* ids, const float* word_emb, const float* pos_emb,
                     const float* gamma, const float* beta, h16* out, int B, int S, int H, int vocab,
-                    int max_pos, int pad_id, float eps, bool fp16, cudaStream_t stream) {
+                    int max_pos, int pad_id, int pos_mode, float eps, bool fp16, cudaStream_t stream) {
     ARB_REQUIRE(ids && word_emb && pos_emb && gamma && beta && out, "embed_ln: null pointer");
     ARB_REQUIRE(B > 0 && S > 0 && S <= 4096, "embed_ln: bad shape B=%d S=%d", B, S);
     if (int rc = check_h(H)) return rc;
     const size_t smem = (S + (S + 31) / 32) * sizeof(int);
     auto kern = fp16 ? embed_ln_kernel<true> : embed_ln_kernel<false>;
     kern<<<B, 256, smem, stream>>>(ids, word_emb, pos_emb, gamma, beta, out, S, H, vocab, max_pos,
-                                   pad_id, eps);
+                                   pad_id, pos_mode, eps);
     ARB_CHECK_CUDA(cudaGetLastError());
     return ARB_OK;
 }

@@ -50,9 +50,15 @@ class B200SentenceEncoder:
 
     def __init__(self, state_dict: dict | None = None, arch: MPNetArch = ALL_MPNET_BASE_V2,
                  device: int | None = None, max_batch: int = 1024, max_seq: int | None = None,
-                 tokenizer=None, seed: int = 0, dtype: str = "bf16"):
+                 tokenizer=None, seed: int = 0, dtype: str = "bf16", model_name: str | None = None):
         torch = _require_cuda()
         self._torch = torch
+        if model_name is not None:  # 'all-mpnet-base-v2' | 'all-MiniLM-L6-v2' (reference CLI choices, :473-475)
+            from .weights import ARCH_BY_MODEL_NAME
+
+            if model_name not in ARCH_BY_MODEL_NAME:
+                raise ValueError(f"model '{model_name}' not supported (have {sorted(ARCH_BY_MODEL_NAME)})")
+            arch = ARCH_BY_MODEL_NAME[model_name]
         self.arch = arch
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.max_seq = int(max_seq or arch.max_seq_length)

@@ -22,7 +22,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-MODEL_NAMES = ("all-mpnet-base-v2",)
+MODEL_NAMES = ("all-mpnet-base-v2", "all-MiniLM-L6-v2")  # the reference's --model choices (:473-475)
 
 _worker_model = None
 _worker_model_name = None
@@ -44,7 +44,11 @@ def init_worker_model(model_name: str):
             raise ValueError(f"model '{model_name}' not supported by the B200 path (have {MODEL_NAMES})")
         from .encoder import B200SentenceEncoder
 
-        _worker_model = B200SentenceEncoder(**_worker_model_kwargs)
+        kwargs = dict(_worker_model_kwargs)
+        kwargs.setdefault("model_name", model_name)
+        if "arch" in kwargs:  # an explicit architecture (tests) wins over the name lookup
+            kwargs.pop("model_name")
+        _worker_model = B200SentenceEncoder(**kwargs)
         _worker_model_name = model_name
 
 

@@ -69,6 +69,10 @@ typedef struct ArbMpnetConfig {
                                                16-bit format of weights + activations in HBM and
                                                of the tensor-core operands; accumulation, softmax
                                                and LayerNorm statistics are always fp32 */
+    int32_t position_mode;                  /* 0 = MPNet: padding-aware position ids (modeling_mpnet.py:889-897);
+                                               1 = BERT: absolute index (all-MiniLM-L6-v2; token-type row 0 is
+                                               folded into the position table by the caller). A BERT-style
+                                               encoder also sets relative_attention_num_buckets = 0. */
 } ArbMpnetConfig;
 
 /* All pointers are HOST fp32 arrays in the nn.Module layouts ([out,in] for Linear weights). */
@@ -118,6 +122,9 @@ int arb_topk_search(const void* queries_dev, const void* corpus_dev, int32_t dty
 /* Merge G sorted per-shard lists (e.g. the all-gathered [G,Q,k] of a row-sharded corpus). */
 int arb_topk_merge(const float* scores_dev, const int64_t* ids_dev, int32_t G, int64_t Q, int32_t k,
                    float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+/* out[i] = cos(emb[i], emb[i-1]) for fp32 rows [n, D] (out[0] = 1): the adjacent-sentence similarity
+ * TextChunker._chunk_semantic computes with _cosine_similarity (text_processor.py:1547-1561, :1601-1605). */
+int arb_adjacent_cosine(const float* emb_dev, int64_t n, int32_t D, float* out_dev, void* stream);
 /* Number of kernel launches one arb_topk_search call enqueues. */
 int arb_topk_search_launches(int32_t dtype);
 
@@ -140,8 +147,8 @@ int arb_gemm16_residual_ln(const void* A, int64_t lda, const void* B, int64_t ld
                            void* stream);
 int arb_embed_layernorm(const int32_t* ids, const float* word_emb, const float* pos_emb,
                         const float* gamma, const float* beta, void* out16, int32_t B, int32_t S,
-                        int32_t H, int32_t vocab, int32_t max_pos, int32_t pad_id, float eps,
-                        int32_t dtype, void* stream);
+                        int32_t H, int32_t vocab, int32_t max_pos, int32_t pad_id, int32_t position_mode,
+                        float eps, int32_t dtype, void* stream);
 int arb_layernorm16(const void* x, const float* gamma, const float* beta, void* out, int64_t rows,
                     int32_t H, float eps, int32_t dtype, void* stream);
 int arb_attention16(const void* qkv, const float* rel_bias, int32_t max_rel, const int32_t* mask,

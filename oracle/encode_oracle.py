@@ -41,9 +41,21 @@ def mpnet_config(arch):
 def reference_model(arch, state_dict: dict):
     """The reference dependency itself: transformers.MPNetModel(add_pooling_layer=False), fp32,
     eval, loaded with `state_dict` (numpy or torch values under HF names)."""
-    from transformers import MPNetModel
+    if getattr(arch, "kind", "mpnet") == "bert":
+        # all-MiniLM-L6-v2 is a BertModel (the reference's second encode site,
+        # 3-chunks/pipeline/src/processors/text_processor.py:853-885, :1379-1396)
+        from transformers import BertConfig, BertModel
 
-    model = MPNetModel(mpnet_config(arch), add_pooling_layer=False).eval()
+        cfg = BertConfig(vocab_size=arch.vocab_size, hidden_size=arch.hidden_size, num_hidden_layers=arch.num_layers,
+                         num_attention_heads=arch.num_heads, intermediate_size=arch.intermediate_size,
+                         max_position_embeddings=arch.max_position_embeddings, layer_norm_eps=arch.layer_norm_eps,
+                         hidden_act="gelu", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                         pad_token_id=arch.pad_token_id, type_vocab_size=2)
+        model = BertModel(cfg, add_pooling_layer=False).eval()
+    else:
+        from transformers import MPNetModel
+
+        model = MPNetModel(mpnet_config(arch), add_pooling_layer=False).eval()
     sd = {k: torch.as_tensor(np.asarray(v)).float() if not torch.is_tensor(v) else v.float()
           for k, v in state_dict.items()}
     missing, unexpected = model.load_state_dict(sd, strict=False)

@@ -32,8 +32,8 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_struct_layout_matches_header():
-    # ArbMpnetConfig: 8 x int32, float, int32; layer weights: 16 pointers; weights: 6 pointers
-    assert C.sizeof(_lib.MpnetConfig) == 40
+    # ArbMpnetConfig: 8 x int32, float, 2 x int32; layer weights: 16 pointers; weights: 6 pointers
+    assert C.sizeof(_lib.MpnetConfig) == 44
     assert C.sizeof(_lib.MpnetLayerWeights) == 16 * C.sizeof(C.c_void_p)
     assert C.sizeof(_lib.MpnetWeights) == 6 * C.sizeof(C.c_void_p)
 

@@ -164,8 +164,47 @@ def test_reference_worker_api(cuda, full_model):
     assert len(out) == len(ref) == 23
     assert _cos(np.stack(out), np.stack(ref)).min() >= COS_TOL
     with pytest.raises(ValueError):
-        generation.init_worker_model("all-MiniLM-L6-v2")  # not built yet: fail loudly, no fallback
+        generation.init_worker_model("all-distilroberta-v1")  # unknown model: fail loudly, no fallback
     generation.configure_worker_model()
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+def test_minilm_encoder_parity(cuda, dtype):
+    """The reference's second model (`--model all-MiniLM-L6-v2`, generate_embeddings_parallel.py:473-475;
+    the semantic chunker's encoder, text_processor.py:853-885): BERT-style, 6 layers, 384-d, 12
+    heads of 32, absolute positions, no relative bias. Oracle: transformers.BertModel + pooling."""
+    from arxiv_rag_b200.weights import ALL_MINILM_L6_V2 as arch
+
+    sd = synthetic_state_dict(arch, 5)
+    ids, mask = eo.synthetic_tokens(10, 70, vocab_size=arch.vocab_size, seed=13, pad_id=arch.pad_token_id)
+    ids[7], mask[7] = arch.pad_token_id, 0  # all-pad row
+    ref = eo.oracle_encode(eo.reference_model(arch, sd), ids, mask)
+    enc = _encoder(arch, sd, dtype, max_batch=16, max_seq=128)
+    got = enc.encode((ids, mask), batch_size=4, normalize_embeddings=True)
+    assert got.shape == (10, 384) and enc.get_sentence_embedding_dimension() == 384
+    _assert_parity(got, ref, mask, dtype)
+    enc.close()
+    enc2 = _encoder(None, None, "fp16", max_batch=4, max_seq=64, model_name="all-MiniLM-L6-v2")  # by name, synthetic weights
+    assert enc2.arch is arch
+    enc2.close()
+
+
+def test_semantic_breaks_match_reference_rule(cuda):
+    """adjacent-pair cosine + the 0.7 threshold of TextChunker._chunk_semantic
+    (text_processor.py:1555-1561, formula :1601-1605)."""
+    from arxiv_rag_b200 import semantic
+    from oracle import search_oracle as so
+
+    rng = np.random.default_rng(0)
+    e = rng.standard_normal((50, 384)).astype(np.float32)
+    e[10] = e[9] * 3.0 + 0.01 * rng.standard_normal(384)  # nearly parallel, different norm
+    e[20] = -e[19]
+    sim = semantic.adjacent_cosine(e).cpu().numpy()
+    ref = np.array([1.0] + [so.cosine_pairwise(e[i], e[i - 1]) for i in range(1, 50)], np.float32)
+    assert np.abs(sim - ref).max() < 1e-5
+    brk = semantic.semantic_breaks(e)
+    assert not brk[0] and not brk[10] and brk[20]
+    assert (brk[1:] == (ref[1:] < 0.7)).all()
 
 
 def test_errors_raise(cuda, full_model):

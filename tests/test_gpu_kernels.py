@@ -132,7 +132,7 @@ def test_embed_layernorm_and_position_ids(lib, cuda, dt):
     b = torch.randn(H, device=cuda) * 0.1
     out = torch.zeros(B * S, H, device=cuda, dtype=tdt)
     _lib.check(lib.arb_embed_layernorm(ids.data_ptr(), we.data_ptr(), pe.data_ptr(), g.data_ptr(), b.data_ptr(),
-                                       out.data_ptr(), B, S, H, V, P, 1, 1e-5, code, _stream()))
+                                       out.data_ptr(), B, S, H, V, P, 1, 0, 1e-5, code, _stream()))
     m = (ids != 1).int()
     pos = (torch.cumsum(m, 1) * m).long() + 1
     ref = torch.nn.functional.layer_norm(we[ids.long()] + pe[pos], (H,), g, b, 1e-5).reshape(B * S, H)
@@ -157,6 +157,48 @@ def test_pool_normalize(lib, cuda, dt):
     ref = torch.nn.functional.normalize(e, p=2, dim=1)
     assert (out - ref).abs().max().item() < 1e-6
     assert (out[3] == 0).all()
+
+
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+@pytest.mark.parametrize("case", [(3, 64, [64, 1, 17]), (2, 200, [200, 77]), (2, 9, [9, 4])])
+def test_attention_head_dim_32_no_bias(lib, cuda, dt, case):
+    """BertSelfAttention shape of all-MiniLM-L6-v2: 12 heads of 32, no relative-position bias
+    (NULL table), additive mask only."""
+    tdt, code, _ = DT[dt]
+    tol = 1.5e-2 if dt == "bf16" else 2e-3
+    B, S, lens = case
+    nH, dh = 12, 32
+    H = nH * dh
+    torch.manual_seed(8)
+    qkv = torch.randn(B * S, 3 * H, device=cuda).to(tdt)
+    mask = (torch.arange(S, device=cuda)[None, :] < torch.tensor(lens, device=cuda)[:, None]).int().contiguous()
+    ctx = torch.zeros(B * S, H, device=cuda, dtype=tdt)
+    _lib.check(lib.arb_attention16(qkv.data_ptr(), 0, 0, mask.data_ptr(), ctx.data_ptr(), B, S, nH, dh, code, 0, _stream()))
+    q, k, v = [t.float().view(B, S, nH, dh).transpose(1, 2) for t in qkv.split(H, dim=1)]
+    ext = (1.0 - mask[:, None, None, :].float()) * torch.finfo(torch.float32).min
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh) + ext, -1) @ v).transpose(1, 2).reshape(B * S, H)
+    lens_t = torch.tensor(lens, device=cuda)
+    live = (torch.arange(S, device=cuda)[None, :] < lens_t[:, None]).reshape(B * S)
+    assert torch.isfinite(ctx.float()).all()
+    assert _rel_err(ctx[live], ref[live]) < tol
+
+
+def test_embed_layernorm_bert_positions(lib, cuda):
+    """position_mode 1: absolute positions (BertEmbeddings), pads included."""
+    torch.manual_seed(9)
+    B, S, V, P, H = 3, 20, 500, 64, 384
+    ids = torch.randint(1, V, (B, S), device=cuda, dtype=torch.int32)
+    ids[1, 5:] = 0
+    we = torch.randn(V, H, device=cuda) * 0.02
+    pe = torch.randn(P, H, device=cuda) * 0.02
+    g = torch.randn(H, device=cuda) * 0.1 + 1
+    b = torch.randn(H, device=cuda) * 0.1
+    out = torch.zeros(B * S, H, device=cuda, dtype=torch.float16)
+    _lib.check(lib.arb_embed_layernorm(ids.data_ptr(), we.data_ptr(), pe.data_ptr(), g.data_ptr(), b.data_ptr(),
+                                       out.data_ptr(), B, S, H, V, P, 0, 1, 1e-12, _lib.ARB_DTYPE_F16, _stream()))
+    pos = torch.arange(S, device=cuda)[None, :].expand(B, S)
+    ref = torch.nn.functional.layer_norm(we[ids.long()] + pe[pos], (H,), g, b, 1e-12).reshape(B * S, H)
+    assert _rel_err(out, ref) < 8e-4
 
 
 @pytest.mark.parametrize("impl", [1, 2])

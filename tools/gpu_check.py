@@ -139,7 +139,7 @@ def stage_rowops():
         pe = torch.randn(P, H, device=DEV) * 0.02
         out = torch.zeros(B * S, H, device=DEV, dtype=tdtype(d))
         _lib.check(lib().arb_embed_layernorm(ids.data_ptr(), we.data_ptr(), pe.data_ptr(), g.data_ptr(), b.data_ptr(),
-                                             out.data_ptr(), B, S, H, V, P, 1, 1e-5, dcode(d), stream()))
+                                             out.data_ptr(), B, S, H, V, P, 1, 0, 1e-5, dcode(d), stream()))
         m = (ids != 1).int()
         pos = (torch.cumsum(m, 1) * m).long() + 1
         ref = torch.nn.functional.layer_norm(we[ids.long()] + pe[pos], (H,), g, b, 1e-5).reshape(B * S, H)
