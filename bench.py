@@ -123,7 +123,7 @@ def run_reference(args):
     """--impl reference: the reference's CPU path (restated), bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     import torch
 
     rate0, n0, threads, model, (ids, mask) = cpu_encode_sample(3.0)
@@ -140,14 +140,14 @@ def run_reference(args):
     sample = (f"{n} synthetic {SEQ}-token chunks per step through the restated generate_embeddings_worker/"
               f"_parallel loop (batch_size 200, chunks_per_worker 500) over transformers.MPNetModel fp32, "
               f"{threads} torch threads")
-    print(json.dumps({
+    return ({
         "impl": "reference", "metric": "chunks/sec encoded (MPNet)", "value": val, "unit": "chunks/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"all-mpnet-base-v2 encode, seq {SEQ}, batch {BATCH} (configs[1]); CPU sample of {n} chunks/step"},
         "cpu_baseline": {"value": val, "unit": "chunks/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def run_b200(args):
@@ -324,8 +324,9 @@ def run_b200(args):
                "sample": f"{n} synthetic {SEQ}-token chunks, restated reference loop (oracle/refpath.py) over "
                          f"transformers.MPNetModel fp32, {threads} torch threads of {os.cpu_count()} host cores"}
 
+    result = None
     if rank == 0:
-        print(json.dumps({
+        result = ({
             "metric": "chunks/sec encoded (MPNet)", "value": value, "unit": "chunks/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -335,9 +336,33 @@ def run_b200(args):
                        "l2": "inputs rotate over 4 batches; per-step activations 6.6 GB >> 126 MB L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "search": search, "unit_norm_check": checksum, "gflop_per_chunk": GFLOP_PER_CHUNK,
-        }), flush=True)
+        })
     if world > 1:
         dist.destroy_process_group()
+    return result
+
+
+class _StdoutGuard:
+    """Keep stdout for the ONE JSON line: while the benchmark runs, file descriptor 1 points at
+    stderr, so native libraries that print to stdout (NCCL's 'NCCL version ...' banner on rank 0)
+    cannot get in front of it."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        import ctypes
+
+        sys.stdout.flush()
+        try:
+            ctypes.CDLL(None).fflush(None)  # drain C stdio buffers (NCCL uses printf) into stderr
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
@@ -349,10 +374,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    with _StdoutGuard():
+        result = run_reference(args) if args.impl == "reference" else run_b200(args)
+    if result is not None:  # rank 0 only: the one JSON line, alone on stdout
+        print(json.dumps(result), flush=True)
 
 
 if __name__ == "__main__":
