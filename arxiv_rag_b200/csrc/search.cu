@@ -8,8 +8,11 @@
 // Work decomposition: item = (corpus split, 128-query tile), split-major, dealt round-robin to a
 // persistent grid so the CTAs running together sweep the same corpus region (L2 reuse). Each
 // epilogue thread owns one query row (one TMEM lane): it scans the 256 scores of every chunk
-// against its current k-th best and inserts the rare survivors into a sorted list in shared
-// memory. Per-item lists go to the workspace and a k-way merge kernel produces the final order.
+// against its k-th best, appends the rare survivors to a small per-row candidate buffer in shared
+// memory, and the buffers are folded into the sorted top-k lists in batches (k <= 16: lists in
+// registers, each thread folds its own buffer; k <= 128: lists in shared memory, merged by the
+// whole warp one row at a time). Per-item lists go to the workspace and a k-way merge kernel
+// produces the final order.
 #include "common.cuh"
 #include "kernels.h"
 #include "tmap.cuh"
@@ -19,7 +22,7 @@ namespace arb {
 
 constexpr int kSBN = 256;     // corpus rows per chunk (MMA N)
 constexpr int kMaxK = 128;    // k <= 16: lists in registers; else 128 rows x k x 8 B of shared memory
-// smem ring depth: 4 x 48 KB stages for k <= 16, 3 when the lists need <= 64 KB, else 2
+// smem ring depth: 4 x 48 KB stages for k <= 16, 3 while list + a >= 16-candidate buffer fit, else 2
 
 struct SearchPlan {
     int nq;        // 128-query tiles
@@ -85,33 +88,55 @@ struct SearchTileIter {
 
 constexpr int kSearchThreads = 192;  // TMA warp, MMA warp, 4 epilogue warps (one per TMEM lane quarter)
 
-// k > 16: each row's sorted list lives in shared memory ([row][k], row-major) and ONE candidate at
-// a time is inserted by the whole warp: every lane owns list slots lane, lane+32, ... (k <= 128),
-// the insert position is a ballot count of the slots >= v (so equal scores keep arrival = id
-// order), and the tail is shifted down by one slot in parallel. Returns the row's new k-th best.
-__device__ __forceinline__ float warp_list_insert(float* ls, int* li, int k, float v, int id, int lane) {
+// k > 16: each row's sorted list lives in shared memory ([row][k], row-major) next to a small
+// unsorted candidate buffer ([row][cbuf]) that the row's own thread appends to. When a buffer is
+// full the whole warp merges it into the list in one pass: every lane owns list slots lane,
+// lane+32, ... (k <= 128) and one candidate; a list entry moves down by the number of candidates
+// that beat it, a candidate lands at (#list entries >= it) + (its rank among the candidates), so
+// equal scores keep arrival (= ascending id) order. All reads precede all writes. Returns the
+// row's new k-th best. Amortised cost per candidate is ~1/cbuf of a single-element insertion.
+__device__ __noinline__ float warp_list_merge(float* ls, int* li, int k, const float* cs, const int* ci,
+                                              int n, int lane) {
+    __syncwarp();  // the owner's buffer stores are visible to the warp
     float s[4];
-    int d[4];
-    int pos = 0;
+    int d[4], adv[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const int i = lane + 32 * t;
         s[t] = i < k ? ls[i] : -INFINITY;
         d[t] = i < k ? li[i] : -1;
-        pos += __popc(__ballot_sync(0xffffffff, s[t] >= v));
+        adv[t] = 0;
+    }
+    const bool has = lane < n;
+    const float cv = has ? cs[lane] : -INFINITY;
+    const int cid = has ? ci[lane] : -1;
+    int crank = 0;
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+        const float sj = cs[j];  // broadcast read
+#pragma unroll
+        for (int t = 0; t < 4; ++t) adv[t] += sj > s[t] ? 1 : 0;
+        crank += (sj > cv || (sj == cv && j < lane)) ? 1 : 0;
+    }
+    int lo = 0, hi = k;  // first list index whose score is < cv (the list is descending)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ls[mid] >= cv) lo = mid + 1;
+        else hi = mid;
     }
     __syncwarp();  // every slot has been read before any slot is overwritten
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const int i = lane + 32 * t;
-        if (i >= pos && i + 1 < k) {
-            ls[i + 1] = s[t];
-            li[i + 1] = d[t];
+        const int p = i + adv[t];
+        if (i < k && p < k) {
+            ls[p] = s[t];
+            li[p] = d[t];
         }
     }
-    if (lane == 0) {
-        ls[pos] = v;
-        li[pos] = id;
+    if (has && lo + crank < k) {
+        ls[lo + crank] = cv;
+        li[lo + crank] = cid;
     }
     __syncwarp();
     return ls[k - 1];
@@ -141,7 +166,7 @@ __global__ void __launch_bounds__(kSearchThreads, 1)
 search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                    const __grid_constant__ CUtensorMap tmap_c, float* __restrict__ part_scores,
                    int32_t* __restrict__ part_ids, int64_t Q, int64_t N, int D, int k, int nq, int cps,
-                   int nchunks, int nsplit) {
+                   int nchunks, int nsplit, int cbuf) {
     using SM = PipeSmem<kSBN, kSStages>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     SM sm{smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)};
@@ -161,10 +186,19 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     } else {
         const int lane_grp = warp & 3;
         const int trow = lane_grp * 32 + lane;  // row of the 128-query tile owned by this thread
-        float* ls_all = reinterpret_cast<float*>(sm.extra());                    // [128][k] (KR == 0)
-        int* li_all = reinterpret_cast<int*>(sm.extra() + static_cast<size_t>(k) * kBM * 4);
-        float* ls = ls_all + trow * k;
-        int* li = li_all + trow * k;
+        // shared memory after the ring: [128][k] list scores, [128][k] list ids (KR == 0 only), then
+        // the candidate buffers [128][cstride] scores and ids (odd stride: conflict-free appends)
+        const int lk = KR > 0 ? 0 : k;
+        const int cstride = cbuf > 1 ? cbuf + 1 : cbuf;
+        float* ls_all = reinterpret_cast<float*>(sm.extra());
+        int* li_all = reinterpret_cast<int*>(sm.extra() + static_cast<size_t>(lk) * kBM * 4);
+        float* ls = ls_all + trow * lk;
+        int* li = li_all + trow * lk;
+        float* cbs_all = reinterpret_cast<float*>(sm.extra() + static_cast<size_t>(lk) * kBM * 8);
+        int* cbi_all = reinterpret_cast<int*>(sm.extra() + static_cast<size_t>(lk) * kBM * 8 +
+                                              static_cast<size_t>(cstride) * kBM * 4);
+        float* cbs = cbs_all + trow * cstride;
+        int* cbi = cbi_all + trow * cstride;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -187,7 +221,36 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 }
                 __syncwarp();  // lists are touched by the whole warp from here on
             }
+            // Survivors of the scan are appended to the row's buffer by its own thread; `thr` is the
+            // row's k-th best as of the last merge (stale = lower, so nothing is ever missed).
             float thr = -INFINITY;
+            int cnt = 0;
+            // KR == 0: merge the buffers of the rows in `m` into their lists, one row at a time, whole warp
+            auto flush = [&](unsigned m) {
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int row = lane_grp * 32 + src;
+                    const int n = __shfl_sync(0xffffffff, cnt, src);
+                    const float nt = warp_list_merge(ls_all + row * k, li_all + row * k, k, cbs_all + row * cstride,
+                                                     cbi_all + row * cstride, n, lane);
+                    if (lane == src) {
+                        thr = nt;
+                        cnt = 0;
+                    }
+                }
+            };
+            // KR > 0: every thread folds its own buffer into its register list; the 32 rows of the
+            // warp advance together, so the cost is the longest buffer, not the sum
+            auto drain = [&]() {
+                const int longest = __reduce_max_sync(0xffffffff, cnt);
+                for (int i = 0; i < longest; ++i) {
+                    const bool on = i < cnt;
+                    reg_insert<KRA>(rs, ri, on ? cbs[i] : -INFINITY, on ? cbi[i] : -1);
+                }
+                cnt = 0;
+                thr = rs[KRA - 1];
+            };
             for (int chunk = c_begin; chunk < c_end; ++chunk) {
                 mbar_wait(sm.tmem_full(acc), acc_phase);
                 tc_fence_after();
@@ -205,28 +268,42 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         mx = fmaxf(mx, (full || c0 + j < nvalid) ? __uint_as_float(r[j]) : -INFINITY);
-                    const float kth = KR > 0 ? rs[KRA - 1] : thr;
-                    if (!__any_sync(0xffffffff, mx > kth)) return;
+                    if (!__any_sync(0xffffffff, mx > thr)) return;
+                    // columns of this row that beat its (possibly stale) k-th best
+                    unsigned pass = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) pass |= (__uint_as_float(r[j]) > thr ? 1u : 0u) << j;
+                    if (!full) pass &= (1u << (nvalid - c0)) - 1u;
+                    const int np = __popc(pass);
+                    // make room first: rows whose buffer cannot take this block's survivors
                     if (KR > 0) {
+                        if (__any_sync(0xffffffff, cnt + np > cbuf)) drain();  // cbuf == 32 >= np
+                    } else {
+                        const unsigned tight = __ballot_sync(0xffffffff, cnt > 0 && cnt + np > cbuf);
+                        if (tight) flush(tight);
+                    }
+                    if (KR > 0 || !__any_sync(0xffffffff, np > cbuf)) {
+                        // common case: append without any further warp synchronisation
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            float v = __uint_as_float(r[j]);
-                            if (!full && c0 + j >= nvalid) v = -INFINITY;
-                            if (__any_sync(0xffffffff, v > rs[KRA - 1])) reg_insert<KRA>(rs, ri, v, id0 + j);
+                            if (pass & (1u << j)) {
+                                cbs[cnt] = __uint_as_float(r[j]);
+                                cbi[cnt] = id0 + j;
+                                ++cnt;
+                            }
                         }
                     } else {
+                        // a row has more survivors than a whole buffer holds (list still filling up,
+                        // or a small buffer beside a large k): append one column at a time
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float v = __uint_as_float(r[j]);
-                            unsigned m = __ballot_sync(0xffffffff, (full || c0 + j < nvalid) && v > thr);
-                            while (m) {  // one candidate (= one row of this warp) at a time, all lanes cooperating
-                                const int src = __ffs(m) - 1;
-                                m &= m - 1;
-                                const float cv = __shfl_sync(0xffffffff, v, src);
-                                const int row = lane_grp * 32 + src;
-                                const float nt = warp_list_insert(ls_all + row * k, li_all + row * k, k, cv, id0 + j, lane);
-                                if (lane == src) thr = nt;
+                            if ((pass & (1u << j)) && __uint_as_float(r[j]) > thr) {
+                                cbs[cnt] = __uint_as_float(r[j]);
+                                cbi[cnt] = id0 + j;
+                                ++cnt;
                             }
+                            const unsigned m = __ballot_sync(0xffffffff, cnt == cbuf);
+                            if (m) flush(m);
                         }
                     }
                 };
@@ -248,6 +325,9 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     acc_phase ^= 1;
                 }
             }
+            // fold in what is still buffered
+            if (KR > 0) drain();
+            else flush(__ballot_sync(0xffffffff, cnt > 0));
             // publish this item's list: part[split][query][k]
             const int64_t qrow = static_cast<int64_t>(qt) * kBM + trow;
             if (qrow < Q) {
@@ -383,18 +463,31 @@ int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int6
         set_error("search: cuTensorMapEncodeTiled failed");
         return ARB_ERR_CUDA;
     }
-    auto launch = [&](auto kern, int stages_bytes, int list_bytes) -> int {
-        const int smem = stages_bytes + list_bytes + 1024;
+    constexpr int kSmemMax = 227 * 1024;
+    // Shared memory after the ring, in (score, id) slots of 8 B per query row: `lk` sorted-list
+    // slots (0 when the list lives in registers) + the candidate buffer. The buffer holds `cbuf`
+    // candidates (even, <= 32) at a row stride of cbuf + 1 slots; when not even 2 fit, 1 at stride 1.
+    auto buffer_for = [&](int ring_bytes, int lk) {
+        const int fit = (kSmemMax - 1024 - ring_bytes) / (kBM * 8) - lk;  // slots left for the buffer
+        const int c = ((fit - 1) & ~1) < 32 ? ((fit - 1) & ~1) : 32;
+        return c >= 2 ? c : 1;
+    };
+    auto launch = [&](auto kern, int ring_bytes, int lk, int cbuf) -> int {
+        const int slots = lk + (cbuf > 1 ? cbuf + 1 : cbuf);
+        const int smem = ring_bytes + slots * kBM * 8 + 1024;
         ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         kern<<<p.grid, kSearchThreads, smem, stream>>>(tq, tc, part_scores, part_ids, Q, N, D, k, p.nq, p.cps,
-                                                       p.nchunks, p.nsplit);
+                                                       p.nchunks, p.nsplit, cbuf);
         return ARB_OK;
     };
+    constexpr int kRing4 = PipeSmem<kSBN, 4>::kExtraOffset, kRing3 = PipeSmem<kSBN, 3>::kExtraOffset,
+                  kRing2 = PipeSmem<kSBN, 2>::kExtraOffset;
+    static_assert((kSmemMax - 1024 - kRing4) / (kBM * 8) >= 33, "register-list kernels need a 32-candidate buffer");
     int lrc;
-    if (k <= 10) lrc = launch(search_topk_kernel<4, 10>, PipeSmem<kSBN, 4>::kExtraOffset, 0);
-    else if (k <= 16) lrc = launch(search_topk_kernel<4, 16>, PipeSmem<kSBN, 4>::kExtraOffset, 0);
-    else if (k <= 64) lrc = launch(search_topk_kernel<3, 0>, PipeSmem<kSBN, 3>::kExtraOffset, k * kBM * 8);
-    else lrc = launch(search_topk_kernel<2, 0>, PipeSmem<kSBN, 2>::kExtraOffset, k * kBM * 8);
+    if (k <= 10) lrc = launch(search_topk_kernel<4, 10>, kRing4, 0, 32);
+    else if (k <= 16) lrc = launch(search_topk_kernel<4, 16>, kRing4, 0, 32);
+    else if (buffer_for(kRing3, k) >= 16) lrc = launch(search_topk_kernel<3, 0>, kRing3, k, buffer_for(kRing3, k));
+    else lrc = launch(search_topk_kernel<2, 0>, kRing2, k, buffer_for(kRing2, k));
     if (lrc) return lrc;
     ARB_CHECK_CUDA(cudaGetLastError());
     return launch_merge_impl<int32_t>(part_scores, part_ids, p.nsplit, Q, k, id_offset, out_scores,

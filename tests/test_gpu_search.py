@@ -45,7 +45,8 @@ def test_golden_small_d32(cuda):
 
 @pytest.mark.parametrize("bf16", [True, False])
 @pytest.mark.parametrize("shape", [(5, 300, 10), (130, 5000, 10), (257, 20000, 100), (3, 7, 10), (1, 1, 1),
-                                   (1000, 10000, 10), (64, 3000, 128)])
+                                   (1000, 10000, 10), (64, 3000, 128), (70, 4000, 17), (200, 30000, 64),
+                                   (129, 9000, 65), (40, 50000, 100), (16, 2500, 127)])
 def test_oracle_parity(cuda, bf16, shape):
     """Ragged Q (not a multiple of 128), N not a multiple of 256, k > N, planted exact duplicates
     (tie rule: ascending id) and near-duplicates (inside the 1e-5 tolerance)."""
@@ -68,6 +69,23 @@ def test_exact_duplicates_order_by_id(cuda):
     s, i = _run(q, c, 6, bf16=True)
     assert i[0, :5].tolist() == [5, 17, 300, 301, 599]
     assert np.ptp(s[0, :5]) == 0.0  # identical rows -> bit-identical scores
+
+
+@pytest.mark.parametrize("k", [24, 40, 100])
+def test_many_duplicates_buffered_lists(cuda, k):
+    """k > 16 keeps candidates in a per-row buffer that is merged into the sorted list in
+    batches: blocks of identical rows (more of them than k, scattered over several 256-row
+    chunks) must still come back in ascending-id order, and the cut at k must keep the lowest ids."""
+    rng = np.random.default_rng(k)
+    c = so.synthetic_unit_rows(3000, 768, seed=6, bf16=True)
+    dup = np.sort(rng.choice(3000, size=k + 37, replace=False))
+    c[dup] = c[dup[0]]
+    q = np.concatenate([c[dup[0]:dup[0] + 1], so.synthetic_unit_rows(4, 768, seed=7, bf16=True)])
+    s, i = _run(q, c, k, bf16=True)
+    assert i[0].tolist() == dup[:k].tolist()
+    assert np.ptp(s[0]) == 0.0
+    rep = so.check_topk(s, i, q, c, k, tol=TOL)
+    assert rep["ok"], rep
 
 
 def test_cfg1_reference_case(cuda):

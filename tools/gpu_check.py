@@ -336,7 +336,38 @@ def stage_perf():
     return True
 
 
-STAGES = {"gemm": stage_gemm, "gemmln": stage_gemmln, "rowops": stage_rowops, "attention": stage_attention, "search": stage_search,
+def stage_searchperf():
+    """Search only: small-shard / small-Q (HBM-bound, the 8-GPU regime) and large-k cases, plus a
+    per-kernel breakdown of one call from the CUPTI activity records (torch.profiler)."""
+    shapes = [(1, 625_000, 10), (64, 625_000, 10), (64, 5_000_000, 10), (512, 625_000, 10), (1024, 1_000_000, 32),
+              (1024, 1_000_000, 64), (1024, 1_000_000, 100), (8192, 2_500_000, 100), (1024, 1_000_000, 128)]
+    for (Q, N, k) in shapes:
+        c = torch.nn.functional.normalize(torch.randn(N, 768, device=DEV), dim=1).to(torch.bfloat16)
+        q = torch.nn.functional.normalize(torch.randn(Q, 768, device=DEV), dim=1).to(torch.bfloat16)
+        need = lib().arb_topk_search_workspace_bytes(_lib.ARB_DTYPE_BF16, Q, N, 768, k)
+        ws = torch.empty(max(need, 256), dtype=torch.uint8, device=DEV)
+        os_ = torch.zeros(Q, k, device=DEV)
+        oi = torch.zeros(Q, k, device=DEV, dtype=torch.int64)
+        call = lambda: _lib.check(lib().arb_topk_search(q.data_ptr(), c.data_ptr(), _lib.ARB_DTYPE_BF16, Q, N, 768, k, os_.data_ptr(),
+                                                        oi.data_ptr(), 0, ws.data_ptr(), ws.numel(), stream()))
+        ms = _time(call, iters=10, warm=3)
+        fl = 2.0 * Q * N * 768
+        print(f"search Q{Q} N{N} k{k}: {ms:.3f} ms {Q / ms * 1e3:.0f} q/s {fl / ms / 1e9:.1f} TFLOP/s corpus {N * 768 * 2 / ms / 1e6:.0f} GB/s",
+              flush=True)
+        if (Q, N) in ((64, 625_000), (1024, 1_000_000)):
+            from torch.profiler import ProfilerActivity, profile
+
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for _ in range(5):
+                    call()
+                torch.cuda.synchronize()
+            for ev in prof.key_averages():
+                print(f"    {ev.key[:70]:70s} n={ev.count} avg {ev.device_time_total / max(ev.count, 1):.1f} us", flush=True)
+        del c, q, ws
+    return True
+
+
+STAGES = {"searchperf": stage_searchperf, "gemm": stage_gemm, "gemmln": stage_gemmln, "rowops": stage_rowops, "attention": stage_attention, "search": stage_search,
           "encode": stage_encode, "perf": stage_perf}
 
 if __name__ == "__main__":
