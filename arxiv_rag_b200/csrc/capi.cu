@@ -308,6 +308,15 @@ int arb_topk_merge(const float* scores_dev, const int64_t* ids_dev, int32_t G, i
                              static_cast<cudaStream_t>(stream));
 }
 
+size_t arb_topk_record_bytes(int64_t Q, int32_t k) { return Q > 0 && k > 0 ? topk_record_bytes(Q, k) : 0; }
+size_t arb_topk_record_ids_offset(int64_t Q, int32_t k) { return Q > 0 && k > 0 ? topk_record_ids_offset(Q, k) : 0; }
+
+int arb_topk_merge_records(const void* records_dev, int32_t G, int64_t Q, int32_t k, float* out_scores_dev,
+                           int64_t* out_ids_dev, void* stream) {
+    return launch_topk_merge_records(records_dev, G, Q, k, out_scores_dev, out_ids_dev,
+                                     static_cast<cudaStream_t>(stream));
+}
+
 static int dtype16(int32_t dtype, bool* fp16) {
     ARB_REQUIRE(dtype == ARB_DTYPE_BF16 || dtype == ARB_DTYPE_F16, "dtype %d must be ARB_DTYPE_BF16 or ARB_DTYPE_F16", dtype);
     *fp16 = dtype == ARB_DTYPE_F16;

@@ -67,5 +67,11 @@ int launch_search_f32(const float* q, const float* corpus, int64_t Q, int64_t N,
 // k-way merge of G per-shard top-k lists: [G,Q,k] -> [Q,k], order (score desc, id asc).
 int launch_topk_merge(const float* scores, const int64_t* ids, int G, int64_t Q, int k,
                       float* out_scores, int64_t* out_ids, cudaStream_t stream);
+// One rank's [Q,k] result as a single buffer (fp32 scores, then 8-byte aligned int64 ids), and the
+// merge of G such records laid end to end (what one all-gather of the records produces).
+size_t topk_record_ids_offset(int64_t Q, int k);
+size_t topk_record_bytes(int64_t Q, int k);
+int launch_topk_merge_records(const void* records, int G, int64_t Q, int k, float* out_scores,
+                              int64_t* out_ids, cudaStream_t stream);
 
 }  // namespace arb

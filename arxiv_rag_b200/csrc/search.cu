@@ -353,12 +353,214 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
 }
 
 // ----------------------------------------------------------------------------- k-way merge
-// One warp per query. Every input list is sorted by (score desc, id asc); lane l owns lists
+// Every input list is sorted by (score desc, id asc). List g of query q starts at
+// scores + g * stride_s + q * k (ids likewise with stride_i), so the same kernels merge the search
+// kernel's per-split lists and the per-rank records of an all-gather.
+//
+// One 128-thread block per query copies its G*k entries to shared memory in one sweep of
+// independent loads. Then, normally, a pruned rank-by-counting merge: the k-th best of the lists'
+// first ceil(k/G) entries is a lower bound tau of the global k-th best; the few entries not behind
+// tau (>= k of them, usually < 2k) are compacted and each finds its output slot by counting the
+// candidates ahead of it — no serial pick-the-best rounds. If the candidate set is large (skewed
+// lists) or the lists are too short to give a bound, a pairwise tree merge takes over:
+// ceil(log2 G) levels, ping-pong between two buffers, every entry locating its slot by a binary
+// search in the partner list.
+constexpr int kMergeThreads = 128;
+constexpr int kMergeCandCap = 512;
+
+template <typename IdT>
+__device__ __forceinline__ bool sorts_ahead(float sa, IdT ia, float sb, IdT ib) {
+    return sa > sb || (sa == sb && ia < ib);
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(kMergeThreads)
+topk_tree_merge_kernel(const float* __restrict__ scores, const IdT* __restrict__ ids, int G, int64_t stride_s,
+                       int64_t stride_i, int64_t Q, int k, int64_t id_offset, float* __restrict__ out_scores,
+                       int64_t* __restrict__ out_ids) {
+    extern __shared__ __align__(16) uint8_t s_merge[];
+    const int tid = threadIdx.x;
+    const int64_t q = blockIdx.x;
+    const int n = G * k, half = ((G + 1) / 2) * k;
+    // buffers: ids A[n], ids B[half], scores A[n], scores B[half], list lengths A[G], B[(G+1)/2]
+    IdT* idA = reinterpret_cast<IdT*>(s_merge);
+    IdT* idB = idA + n;
+    float* scA = reinterpret_cast<float*>(idB + half);
+    float* scB = scA + n;
+    int* lenA = reinterpret_cast<int*>(scB + half);
+    int* lenB = lenA + G;
+    int* offs = lenB + (G + 1) / 2;  // [G + 1] candidate counts -> offsets (pruned path)
+    __shared__ int sh_tau, sh_total;
+    if (tid == 0) sh_tau = -1;
+    {
+        constexpr int U = 8;  // independent loads in flight per thread
+        for (int e0 = 0; e0 < n; e0 += kMergeThreads * U) {
+            float fs[U];
+            IdT fi[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * kMergeThreads + tid;
+                if (e < n) {
+                    const int g = e / k, p = e - g * k;
+                    fs[u] = scores[g * stride_s + q * k + p];
+                    fi[u] = ids[g * stride_i + q * k + p];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * kMergeThreads + tid;
+                if (e < n) {
+                    scA[e] = fs[u];
+                    idA[e] = fi[u];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // valid length of every list (unused slots, id < 0, sit at the tail)
+    for (int g = tid; g < G; g += kMergeThreads) {
+        int lo = 0, hi = k;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (idA[g * k + mid] >= 0) lo = mid + 1;
+            else hi = mid;
+        }
+        lenA[g] = lo;
+    }
+    __syncthreads();
+    const int m = (k + G - 1) / G;
+    if (G > 1 && G * m <= half) {
+        // tau = the entry of rank k-1 among the first m entries of every list (set S). S is copied
+        // to a flat array first so that the rank count is one pipelined sweep.
+        const int ns = G * m;
+        for (int e = tid; e < ns; e += kMergeThreads) {
+            const int g = e / m, p = e - g * m;
+            const bool valid = p < lenA[g];
+            scB[e] = valid ? scA[g * k + p] : -INFINITY;
+            idB[e] = valid ? idA[g * k + p] : static_cast<IdT>(-1);
+        }
+        __syncthreads();
+        for (int e = tid; e < ns; e += kMergeThreads) {
+            const float s = scB[e];
+            const IdT id = idB[e];
+            if (id < 0) continue;
+            int ahead = 0;
+#pragma unroll 4
+            for (int j = 0; j < ns; ++j) ahead += sorts_ahead<IdT>(scB[j], idB[j], s, id) ? 1 : 0;
+            if (ahead == k - 1) sh_tau = (e / m) * k + (e - (e / m) * m);
+        }
+        __syncthreads();
+        const int tau = sh_tau;
+        if (tau >= 0) {  // block-uniform
+            const float ts = scA[tau];
+            const IdT ti = idA[tau];
+            for (int g = tid; g < G; g += kMergeThreads) {  // entries of list g not behind tau
+                int lo = 0, hi = lenA[g];
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (!sorts_ahead<IdT>(ts, ti, scA[g * k + mid], idA[g * k + mid])) lo = mid + 1;
+                    else hi = mid;
+                }
+                offs[g] = lo;
+            }
+            __syncthreads();
+            if (tid < 32) {  // exclusive scan of the counts
+                int run = 0;
+                for (int b0 = 0; b0 < G; b0 += 32) {
+                    const int g = b0 + tid;
+                    const int c = g < G ? offs[g] : 0;
+                    int incl = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int up = __shfl_up_sync(0xffffffff, incl, o);
+                        if (tid >= o) incl += up;
+                    }
+                    if (g < G) offs[g] = run + incl - c;
+                    run += __shfl_sync(0xffffffff, incl, 31);
+                }
+                if (tid == 0) {
+                    offs[G] = run;
+                    sh_total = run;
+                }
+            }
+            __syncthreads();
+            const int C = sh_total;
+            if (C <= kMergeCandCap && C <= half) {  // block-uniform; C >= k by construction
+                for (int g = tid; g < G; g += kMergeThreads) {
+                    const int o = offs[g], c = offs[g + 1] - o;
+                    for (int p = 0; p < c; ++p) {
+                        scB[o + p] = scA[g * k + p];
+                        idB[o + p] = idA[g * k + p];
+                    }
+                }
+                __syncthreads();
+                for (int e = tid; e < C; e += kMergeThreads) {
+                    const float s = scB[e];
+                    const IdT id = idB[e];
+                    int ahead = 0;
+#pragma unroll 4
+                    for (int j = 0; j < C; ++j) ahead += sorts_ahead<IdT>(scB[j], idB[j], s, id) ? 1 : 0;
+                    if (ahead < k) {
+                        out_scores[q * k + ahead] = s;
+                        out_ids[q * k + ahead] = static_cast<int64_t>(id) + id_offset;
+                    }
+                }
+                return;
+            }
+        }
+    }
+    IdT *idS = idA, *idD = idB;
+    float *scS = scA, *scD = scB;
+    int *lenS = lenA, *lenD = lenB;
+    int L = G;
+    while (L > 1) {
+        const int Lo = (L + 1) / 2;
+        for (int e = tid; e < L * k; e += kMergeThreads) {
+            const int g = e / k, p = e - g * k;
+            if (p >= lenS[g]) continue;
+            const float s = scS[e];
+            const IdT id = idS[e];
+            int dst = p;
+            const int pg = g ^ 1;
+            if (pg < L) {  // entries of the partner list that sort ahead of this one
+                const float* ps = scS + pg * k;
+                const IdT* pi = idS + pg * k;
+                int lo = 0, hi = lenS[pg];
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (sorts_ahead<IdT>(ps[mid], pi[mid], s, id)) lo = mid + 1;
+                    else hi = mid;
+                }
+                dst += lo;
+            }
+            if (dst < k) {
+                scD[(g >> 1) * k + dst] = s;
+                idD[(g >> 1) * k + dst] = id;
+            }
+        }
+        for (int g = tid; g < Lo; g += kMergeThreads) {
+            const int both = lenS[2 * g] + (2 * g + 1 < L ? lenS[2 * g + 1] : 0);
+            lenD[g] = both < k ? both : k;
+        }
+        __syncthreads();
+        IdT* ti = idS; idS = idD; idD = ti;
+        float* ts = scS; scS = scD; scD = ts;
+        int* tl = lenS; lenS = lenD; lenD = tl;
+        L = Lo;
+    }
+    const int len = lenS[0];
+    for (int r = tid; r < k; r += kMergeThreads) {
+        out_scores[q * k + r] = r < len ? scS[r] : -INFINITY;
+        out_ids[q * k + r] = r < len ? static_cast<int64_t>(idS[r]) + id_offset : -1;
+    }
+}
+
+// Fallback when G*k entries do not fit in shared memory: one warp per query, lane l owns lists
 // l, l+32, ... and offers the best of their heads each round; a warp arg-max picks the winner.
 template <typename IdT>
 __global__ void __launch_bounds__(256)
-topk_merge_kernel(const float* __restrict__ scores, const IdT* __restrict__ ids, int G, int64_t Q,
-                  int k, int64_t id_offset, float* __restrict__ out_scores,
+topk_merge_kernel(const float* __restrict__ scores, const IdT* __restrict__ ids, int G, int64_t stride_s,
+                  int64_t stride_i, int64_t Q, int k, int64_t id_offset, float* __restrict__ out_scores,
                   int64_t* __restrict__ out_ids) {
     extern __shared__ int s_pos_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -374,9 +576,8 @@ topk_merge_kernel(const float* __restrict__ scores, const IdT* __restrict__ ids,
         for (int g = lane; g < G; g += 32) {
             const int p = pos[g];
             if (p < k) {
-                const int64_t off = (static_cast<int64_t>(g) * Q + q) * k + p;
-                const float s = scores[off];
-                const int64_t id = static_cast<int64_t>(ids[off]);
+                const float s = scores[g * stride_s + q * k + p];
+                const int64_t id = static_cast<int64_t>(ids[g * stride_i + q * k + p]);
                 if (id >= 0 && (bg < 0 || s > bs || (s == bs && id < bi))) {
                     bs = s;
                     bi = id;
@@ -405,16 +606,28 @@ topk_merge_kernel(const float* __restrict__ scores, const IdT* __restrict__ ids,
 }
 
 template <typename IdT>
-static int launch_merge_impl(const float* scores, const IdT* ids, int G, int64_t Q, int k,
-                             int64_t id_offset, float* out_scores, int64_t* out_ids,
+static int launch_merge_impl(const float* scores, const IdT* ids, int G, int64_t stride_s, int64_t stride_i,
+                             int64_t Q, int k, int64_t id_offset, float* out_scores, int64_t* out_ids,
                              cudaStream_t stream) {
-    const int warps = 8;
-    const size_t smem = static_cast<size_t>(warps) * G * sizeof(int);
-    ARB_REQUIRE(smem <= 48 * 1024, "topk_merge: too many lists (G=%d)", G);
-    const int64_t blocks = (Q + warps - 1) / warps;
-    ARB_REQUIRE(blocks < (1ll << 31), "topk_merge: Q too large");
-    topk_merge_kernel<IdT><<<static_cast<int>(blocks), warps * 32, smem, stream>>>(
-        scores, ids, G, Q, k, id_offset, out_scores, out_ids);
+    constexpr size_t kMergeSmemMax = 200 * 1024;
+    const size_t n = static_cast<size_t>(G) * k, half = static_cast<size_t>((G + 1) / 2) * k;
+    const size_t tree = (n + half) * (sizeof(IdT) + 4) + (static_cast<size_t>(G) * 2 + (G + 1) / 2 + 1) * 4;
+    if (tree <= kMergeSmemMax) {
+        ARB_REQUIRE(Q < (1ll << 31), "topk_merge: Q too large");
+        auto kern = topk_tree_merge_kernel<IdT>;
+        if (tree > 48 * 1024)
+            ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tree)));
+        kern<<<static_cast<int>(Q), kMergeThreads, tree, stream>>>(scores, ids, G, stride_s, stride_i, Q, k, id_offset,
+                                                                   out_scores, out_ids);
+    } else {
+        int warps = 8;
+        while (warps > 1 && static_cast<size_t>(warps) * G * 4 > 48 * 1024) warps >>= 1;
+        ARB_REQUIRE(static_cast<size_t>(warps) * G * 4 <= 48 * 1024, "topk_merge: too many lists (G=%d)", G);
+        const int64_t blocks = (Q + warps - 1) / warps;
+        ARB_REQUIRE(blocks < (1ll << 31), "topk_merge: Q too large");
+        topk_merge_kernel<IdT><<<static_cast<int>(blocks), warps * 32, static_cast<size_t>(warps) * G * 4, stream>>>(
+            scores, ids, G, stride_s, stride_i, Q, k, id_offset, out_scores, out_ids);
+    }
     ARB_CHECK_CUDA(cudaGetLastError());
     return ARB_OK;
 }
@@ -423,7 +636,25 @@ int launch_topk_merge(const float* scores, const int64_t* ids, int G, int64_t Q,
                       float* out_scores, int64_t* out_ids, cudaStream_t stream) {
     ARB_REQUIRE(scores && ids && out_scores && out_ids, "topk_merge: null pointer");
     ARB_REQUIRE(G > 0 && Q > 0 && k > 0, "topk_merge: bad shape G=%d Q=%lld k=%d", G, (long long)Q, k);
-    return launch_merge_impl<int64_t>(scores, ids, G, Q, k, 0, out_scores, out_ids, stream);
+    return launch_merge_impl<int64_t>(scores, ids, G, Q * k, Q * k, Q, k, 0, out_scores, out_ids, stream);
+}
+
+// A "record" is one rank's [Q,k] result in one buffer — float32 scores, then (8-byte aligned)
+// int64 ids — so that a single all-gather moves both; records are merged where they land.
+size_t topk_record_ids_offset(int64_t Q, int k) { return (static_cast<size_t>(Q) * k * 4 + 7) / 8 * 8; }
+size_t topk_record_bytes(int64_t Q, int k) { return topk_record_ids_offset(Q, k) + static_cast<size_t>(Q) * k * 8; }
+
+int launch_topk_merge_records(const void* records, int G, int64_t Q, int k, float* out_scores,
+                              int64_t* out_ids, cudaStream_t stream) {
+    ARB_REQUIRE(records && out_scores && out_ids, "topk_merge_records: null pointer");
+    ARB_REQUIRE(G > 0 && Q > 0 && k > 0, "topk_merge_records: bad shape G=%d Q=%lld k=%d", G, (long long)Q, k);
+    ARB_REQUIRE((reinterpret_cast<uintptr_t>(records) & 7) == 0, "topk_merge_records: records must be 8-byte aligned");
+    const size_t rec = topk_record_bytes(Q, k);
+    const uint8_t* base = static_cast<const uint8_t*>(records);
+    return launch_merge_impl<int64_t>(reinterpret_cast<const float*>(base),
+                                      reinterpret_cast<const int64_t*>(base + topk_record_ids_offset(Q, k)), G,
+                                      static_cast<int64_t>(rec / 4), static_cast<int64_t>(rec / 8), Q, k, 0, out_scores,
+                                      out_ids, stream);
 }
 
 // ----------------------------------------------------------------------------- bf16 search
@@ -490,7 +721,7 @@ int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int6
     else lrc = launch(search_topk_kernel<2, 0>, kRing2, k, buffer_for(kRing2, k));
     if (lrc) return lrc;
     ARB_CHECK_CUDA(cudaGetLastError());
-    return launch_merge_impl<int32_t>(part_scores, part_ids, p.nsplit, Q, k, id_offset, out_scores,
+    return launch_merge_impl<int32_t>(part_scores, part_ids, p.nsplit, Q * k, Q * k, Q, k, id_offset, out_scores,
                                       out_ids, stream);
 }
 

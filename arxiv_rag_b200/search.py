@@ -131,8 +131,11 @@ class ShardedCorpusIndex:
     """Row-sharded corpus across the ranks of a torch.distributed process group.
 
     Every rank holds rows `shard_bounds(N, world, rank)` and the full query batch; `search`
-    returns the identical global top-k on every rank: local fused top-k -> all_gather of the
-    `[Q,k]` (score, id) lists -> k-way merge. The only collective on the path is that all_gather.
+    returns the identical global top-k on every rank: local fused top-k written as one record
+    (`[Q,k]` float32 scores + int64 ids in a single buffer) -> ONE all_gather of the records ->
+    k-way merge of the records where they landed. The only collective on the path is that
+    all_gather. `search_graphed` replays the same three steps (search, all_gather, merge) from a
+    CUDA graph per (Q, k), for the latency-bound small-batch regime.
     """
 
     def __init__(self, local_corpus, global_rows: int, group=None, device: int | None = None):
@@ -147,14 +150,75 @@ class ShardedCorpusIndex:
         if n_local != hi - lo:
             raise ValueError(f"rank {self.rank}: local shard has {n_local} rows, expected {hi - lo}")
         self.index = CorpusIndex(local_corpus, id_offset=lo, device=device)
+        self._bufs = {}    # (Q, k) -> (local record, gathered records, out scores, out ids)
+        self._graphs = {}  # (Q, k) -> (graph, static queries)
+
+    def _buffers(self, Q: int, k: int):
+        torch = self.index._torch
+        key = (Q, k)
+        if key not in self._bufs:
+            dev = self.index.corpus.device
+            rec = int(_lib.lib().arb_topk_record_bytes(Q, k))
+            self._bufs[key] = (torch.empty(rec, dtype=torch.uint8, device=dev),
+                               torch.empty(self.world * rec, dtype=torch.uint8, device=dev),
+                               torch.empty((Q, k), dtype=torch.float32, device=dev),
+                               torch.empty((Q, k), dtype=torch.int64, device=dev))
+        return self._bufs[key]
+
+    def _search_into(self, queries, k: int, bufs):
+        torch = self.index._torch
+        local, gathered, out_s, out_i = bufs
+        Q = queries.shape[0]
+        ids_off = int(_lib.lib().arb_topk_record_ids_offset(Q, k))
+        ls = local[:Q * k * 4].view(torch.float32).view(Q, k)
+        li = local[ids_off:ids_off + Q * k * 8].view(torch.int64).view(Q, k)
+        self.index.search(queries, k, out_scores=ls, out_ids=li)
+        self._dist.all_gather_into_tensor(gathered, local, group=self.group)
+        with torch.cuda.device(gathered.device):
+            _lib.check(_lib.lib().arb_topk_merge_records(_lib.ptr(gathered), self.world, Q, k, _lib.ptr(out_s),
+                                                         _lib.ptr(out_i), _lib.current_stream()))
+        return out_s, out_i
 
     def search(self, queries, k: int = 10):
-        torch = self.index._torch
-        ls, li = self.index.search(queries, k)
+        """-> (scores `[Q,k]` float32, ids `[Q,k]` int64), identical on every rank. The returned
+        tensors are reused by the next call with the same (Q, k); clone them to keep them."""
         if self.world == 1:
-            return ls, li
-        gs = torch.empty((self.world,) + tuple(ls.shape), dtype=ls.dtype, device=ls.device)
-        gi = torch.empty((self.world,) + tuple(li.shape), dtype=li.dtype, device=li.device)
-        self._dist.all_gather_into_tensor(gs, ls, group=self.group)
-        self._dist.all_gather_into_tensor(gi, li, group=self.group)
-        return merge_topk(gs, gi)
+            return self.index.search(queries, k)
+        Q = queries.shape[0]
+        if Q == 0:
+            return self.index.search(queries, k)
+        return self._search_into(queries, k, self._buffers(Q, k))
+
+    def search_graphed(self, queries, k: int = 10):
+        """`search` replayed from a CUDA graph (captured on first use per (Q, k); the collective is
+        captured with it). `queries` must be a CUDA tensor of the corpus dtype; every rank must call
+        it with the same shapes in the same order."""
+        torch = self.index._torch
+        Q = queries.shape[0]
+        key = (Q, k)
+        if key not in self._graphs:
+            static_q = torch.empty_like(queries, dtype=self.index.corpus.dtype, device=self.index.corpus.device)
+            static_q.copy_(queries)
+            self.index._workspace(Q, k)  # allocate outside the capture
+            bufs = self._buffers(Q, k) if self.world > 1 else None
+            outs = None if self.world > 1 else (torch.empty((Q, k), dtype=torch.float32, device=static_q.device),
+                                                torch.empty((Q, k), dtype=torch.int64, device=static_q.device))
+
+            def run():
+                if self.world > 1:
+                    return self._search_into(static_q, k, bufs)
+                return self.index.search(static_q, k, out_scores=outs[0], out_ids=outs[1])
+
+            side = torch.cuda.Stream(device=static_q.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                run()  # warm-up outside the capture (lazy NCCL init, function attributes)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                res = run()
+            self._graphs[key] = (g, static_q, res)
+        g, static_q, res = self._graphs[key]
+        static_q.copy_(queries, non_blocking=True)
+        g.replay()
+        return res

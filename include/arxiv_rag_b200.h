@@ -122,6 +122,14 @@ int arb_topk_search(const void* queries_dev, const void* corpus_dev, int32_t dty
 /* Merge G sorted per-shard lists (e.g. the all-gathered [G,Q,k] of a row-sharded corpus). */
 int arb_topk_merge(const float* scores_dev, const int64_t* ids_dev, int32_t G, int64_t Q, int32_t k,
                    float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+/* Row-sharded search moves each rank's result in ONE all-gather: a record is the rank's [Q,k]
+ * float32 scores followed, at arb_topk_record_ids_offset (8-byte aligned), by its [Q,k] int64 ids —
+ * pass those two addresses to arb_topk_search as out_scores_dev / out_ids_dev. arb_topk_merge_records
+ * merges G records laid end to end (the all-gather output), same order rule as arb_topk_merge. */
+size_t arb_topk_record_bytes(int64_t Q, int32_t k);
+size_t arb_topk_record_ids_offset(int64_t Q, int32_t k);
+int arb_topk_merge_records(const void* records_dev, int32_t G, int64_t Q, int32_t k, float* out_scores_dev,
+                           int64_t* out_ids_dev, void* stream);
 /* out[i] = cos(emb[i], emb[i-1]) for fp32 rows [n, D] (out[0] = 1): the adjacent-sentence similarity
  * TextChunker._chunk_semantic computes with _cosine_similarity (text_processor.py:1547-1561, :1601-1605). */
 int arb_adjacent_cosine(const float* emb_dev, int64_t n, int32_t D, float* out_dev, void* stream);

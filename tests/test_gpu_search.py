@@ -97,15 +97,39 @@ def test_cfg1_reference_case(cuda):
     assert rep["ok"] and rep["exact"] >= rep["total"] - 20, rep
 
 
-def test_merge_kernel_matches_oracle(cuda):
+@pytest.mark.parametrize("shape", [(5, 37, 9), (37, 20, 100), (144, 64, 10), (1, 5, 4), (2, 1, 1), (7, 300, 33),
+                                   (300, 3, 128)])
+def test_merge_kernel_matches_oracle(cuda, shape):
+    """k-way merge of sorted lists: the shared-memory tree merge, and (last shape: G*k entries do
+    not fit in shared memory) the one-warp-per-query fallback. Ties inside and across lists, a
+    short list, an empty list."""
     rng = np.random.default_rng(0)
-    G, Q, k = 5, 37, 9
+    G, Q, k = shape
     sc = np.sort(rng.standard_normal((G, Q, k)).astype(np.float32), axis=2)[:, :, ::-1].copy()
-    sc[:, :, 3] = sc[:, :, 2]  # ties inside and across lists
-    sc[1] = sc[0]
+    if k > 3:
+        sc[:, :, 3] = sc[:, :, 2]  # ties inside a list
+    if G > 1:
+        sc[1] = sc[0]  # and across lists
     ids = np.stack([np.sort(rng.choice(10_000, size=(Q, k), replace=False), axis=1) + g * 10_000 for g in range(G)])
-    sc[2, :, 6:] = -np.inf
-    ids[2, :, 6:] = -1  # a short shard
+    if G > 2 and k > 6:
+        sc[2, :, 6:] = -np.inf
+        ids[2, :, 6:] = -1  # a short shard
+    if G > 4:
+        sc[4] = -np.inf
+        ids[4] = -1  # an empty shard
+    ms, mi = S.merge_topk(torch.from_numpy(sc).cuda(), torch.from_numpy(ids).cuda())
+    rs, ri = so.merge_topk(sc, ids)
+    assert np.array_equal(mi.cpu().numpy(), ri) and np.array_equal(ms.cpu().numpy(), rs)
+
+
+def test_merge_skewed_lists_take_the_tree_path(cuda):
+    """One weak list drags the pruning bound down so that (almost) every entry of the other lists
+    is a candidate: more than the pruned path accepts, so the pairwise tree merge must finish."""
+    rng = np.random.default_rng(1)
+    G, Q, k = 64, 6, 128
+    sc = np.sort(rng.uniform(1.0, 2.0, size=(G, Q, k)).astype(np.float32), axis=2)[:, :, ::-1].copy()
+    sc[9] = np.sort(rng.uniform(0.1, 0.5, size=(Q, k)).astype(np.float32), axis=1)[:, ::-1]
+    ids = np.stack([np.sort(rng.choice(100_000, size=(Q, k), replace=False), axis=1) + g * 100_000 for g in range(G)])
     ms, mi = S.merge_topk(torch.from_numpy(sc).cuda(), torch.from_numpy(ids).cuda())
     rs, ri = so.merge_topk(sc, ids)
     assert np.array_equal(mi.cpu().numpy(), ri) and np.array_equal(ms.cpu().numpy(), rs)
@@ -132,6 +156,55 @@ def test_shard_invariance_large(cuda):
     # spot-check against the oracle on a query subset
     rep = so.check_topk(fs[:16].cpu().numpy(), fi[:16].cpu().numpy(), q[:16].float().cpu().numpy(), c.float().cpu().numpy(), k)
     assert rep["ok"], rep
+
+
+@pytest.mark.parametrize("Qk", [(700, 10), (33, 7), (64, 100)])
+def test_record_merge_equals_unsharded(cuda, Qk):
+    """The multi-GPU exchange format: every rank's result written as one record (scores then ids in
+    a single buffer), G records laid end to end as one all-gather leaves them, merged by
+    arb_topk_merge_records == the unsharded search. Odd Q*k exercises the 8-byte id alignment."""
+    from arxiv_rag_b200 import _lib
+
+    Q, k = Qk
+    N, G = 120_000, 5
+    g = torch.Generator(device="cuda").manual_seed(3)
+    c = torch.nn.functional.normalize(torch.randn(N, 768, device=cuda, generator=g), dim=1).to(torch.bfloat16)
+    c[N // 2 + 5] = c[7]  # an exact tie across two shards
+    q = torch.nn.functional.normalize(torch.randn(Q, 768, device=cuda, generator=g), dim=1).to(torch.bfloat16)
+    q[0] = c[7]
+    fs, fi = S.CorpusIndex(c).search(q, k)
+    rec, off = int(_lib.lib().arb_topk_record_bytes(Q, k)), int(_lib.lib().arb_topk_record_ids_offset(Q, k))
+    assert off % 8 == 0 and off >= Q * k * 4 and rec == off + Q * k * 8
+    gathered = torch.zeros(G * rec, dtype=torch.uint8, device=cuda)
+    for r in range(G):
+        lo, hi = S.shard_bounds(N, G, r)
+        ls = gathered[r * rec:r * rec + Q * k * 4].view(torch.float32).view(Q, k)
+        li = gathered[r * rec + off:r * rec + off + Q * k * 8].view(torch.int64).view(Q, k)
+        S.CorpusIndex(c[lo:hi], id_offset=lo).search(q, k, out_scores=ls, out_ids=li)
+    ms = torch.empty((Q, k), dtype=torch.float32, device=cuda)
+    mi = torch.empty((Q, k), dtype=torch.int64, device=cuda)
+    _lib.check(_lib.lib().arb_topk_merge_records(_lib.ptr(gathered), G, Q, k, _lib.ptr(ms), _lib.ptr(mi), _lib.current_stream()))
+    assert torch.equal(mi, fi) and torch.equal(ms, fs)
+    assert fi[0, :2].tolist() == [7, N // 2 + 5]
+
+
+def test_sharded_index_graph_replay(cuda):
+    """ShardedCorpusIndex.search_graphed (world 1 here; the collective joins the same graph when
+    world > 1) replays bit-identical results, also for new queries of the captured shape."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29577", rank=0, world_size=1)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    c = torch.nn.functional.normalize(torch.randn(40_000, 768, device=cuda, generator=g), dim=1).to(torch.bfloat16)
+    idx = S.ShardedCorpusIndex(c, 40_000)
+    for seed in (1, 2):
+        q = torch.nn.functional.normalize(torch.randn(16, 768, device=cuda, generator=g), dim=1).to(torch.bfloat16)
+        es, ei = idx.search(q, 10)
+        gs_, gi_ = idx.search_graphed(q, 10)
+        assert torch.equal(es, gs_) and torch.equal(ei, gi_)
+    assert len(idx._graphs) == 1
+    dist.destroy_process_group()
 
 
 def test_row_permutation_property(cuda):

@@ -354,7 +354,7 @@ def stage_searchperf():
         fl = 2.0 * Q * N * 768
         print(f"search Q{Q} N{N} k{k}: {ms:.3f} ms {Q / ms * 1e3:.0f} q/s {fl / ms / 1e9:.1f} TFLOP/s corpus {N * 768 * 2 / ms / 1e6:.0f} GB/s",
               flush=True)
-        if (Q, N) in ((64, 625_000), (1024, 1_000_000)):
+        if (Q, N) in ((1, 625_000), (64, 625_000), (1024, 1_000_000)):
             from torch.profiler import ProfilerActivity, profile
 
             with profile(activities=[ProfilerActivity.CUDA]) as prof:
