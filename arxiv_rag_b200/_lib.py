@@ -80,6 +80,7 @@ SIGNATURES = {
     "arb_topk_search": (C.c_int, [_VP, _VP, _I32, _I64, _I64, _I32, _I32, _VP, _VP, _I64, _VP, _SZ, _VP]),
     "arb_topk_merge": (C.c_int, [_VP, _VP, _I32, _I64, _I32, _VP, _VP, _VP]),
     "arb_topk_search_launches": (C.c_int, [_I32]),
+    "arb_set_gemm_mode": (C.c_int, [_I32]),
     "arb_topk_record_bytes": (_SZ, [_I64, _I32]),
     "arb_topk_record_ids_offset": (_SZ, [_I64, _I32]),
     "arb_topk_merge_records": (C.c_int, [_VP, _I32, _I64, _I32, _VP, _VP, _VP]),

@@ -308,6 +308,12 @@ int arb_topk_merge(const float* scores_dev, const int64_t* ids_dev, int32_t G, i
                              static_cast<cudaStream_t>(stream));
 }
 
+int arb_set_gemm_mode(int32_t mode) {
+    ARB_REQUIRE(mode >= 0 && mode <= 2, "gemm mode %d must be 0 (auto), 1 (single CTA) or 2 (CTA pairs)", mode);
+    set_gemm_mode(mode);
+    return ARB_OK;
+}
+
 size_t arb_topk_record_bytes(int64_t Q, int32_t k) { return Q > 0 && k > 0 ? topk_record_bytes(Q, k) : 0; }
 size_t arb_topk_record_ids_offset(int64_t Q, int32_t k) { return Q > 0 && k > 0 ? topk_record_ids_offset(Q, k) : 0; }
 

@@ -37,6 +37,29 @@ struct GemmTileIter {
     }
 };
 
+// 0 = auto (pairs when there are more 256-row blocks than CTA pairs), 1 = single CTA, 2 = CTA pairs
+static int g_gemm_mode = 0;
+void set_gemm_mode(int mode) { g_gemm_mode = mode; }
+
+// CTA-pair variant: 256 x 256 tiles, 32 KB per stage and CTA (A 128 x 64 + half of B): 5 stages
+// leave room for double-buffered epilogue staging.
+constexpr int kGemm2Stages = 5;
+using Gemm2Smem = PipeSmem<kGemmBN, kGemm2Stages, 4 * kStageTileBytes, 2>;  // two staging tiles per group
+template <bool k2Cta>
+constexpr int kGemmStageBufs = k2Cta ? 2 : 1;
+
+// Pair schedule: tile t -> (256-row block t / num_n, n-block t % num_n); row_a is this CTA's half.
+struct Gemm2TileIter {
+    int tile, step, tiles, num_n, rank;
+    __device__ __forceinline__ bool next(int& row_a, int& row_b) {
+        if (tile >= tiles) return false;
+        row_a = (tile / num_n) * (2 * kBM) + rank * kBM;
+        row_b = (tile % num_n) * kGemmBN;
+        tile += step;
+        return true;
+    }
+};
+
 // gelu(x) = x * Phi(x) with erf from Abramowitz-Stegun 7.1.28:
 //   1 - erf(z) = (1 + a1 z + ... + a6 z^6)^-16, |err| <= 3e-7, z = |x|/sqrt(2) folded into b_i.
 // One MUFU (rcp) and ~14 FMA-pipe ops per element; |gelu err| <= 8.2e-7 absolute in fp32.
@@ -79,8 +102,9 @@ __device__ __forceinline__ float gelu_tanh_fit(float x) {
     return fmaf(h, t, h);
 }
 
-// OutT = h16 (16-bit activations in the kF16 format) or float.
-template <int EPI, bool kF16, typename OutT>
+// OutT = h16 (16-bit activations in the kF16 format) or float. k2Cta: launched as clusters of two
+// CTAs that share one 256 x 256 tile through tcgen05 cta_group::2 (see umma_pipe.cuh).
+template <int EPI, bool kF16, typename OutT, bool k2Cta>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
@@ -88,34 +112,58 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     constexpr int BN = kGemmBN;
     constexpr int CW = 128 / static_cast<int>(sizeof(OutT));  // columns per staging chunk
     constexpr int CPG = (BN / 2) / CW;                        // chunks per group per tile
+    using SM = typename std::conditional<k2Cta, Gemm2Smem, GemmSmem>::type;
+    using Iter = typename std::conditional<k2Cta, Gemm2TileIter, GemmTileIter>::type;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // SWIZZLE_128B tiles need a 1024-byte aligned base; align by hand (the launcher adds slack).
-    GemmSmem sm{smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)};
+    SM sm{smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)};
     const int warp = __shfl_sync(0xffffffff, threadIdx.x / 32, 0);
     const int lane = threadIdx.x & 31;
+    const int rank = k2Cta ? static_cast<int>(cluster_ctarank()) : 0;
 
-    const int num_m = static_cast<int>((M + kBM - 1) / kBM);
     const int num_n = (N + BN - 1) / BN;
     const int kblocks = (K + kBK - 1) / kBK;
-    GemmTileIter it{static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), num_m * num_n, num_n, BN};
+    Iter it;
+    if constexpr (k2Cta) {
+        const int num_m2 = static_cast<int>((M + 2 * kBM - 1) / (2 * kBM));
+        it = Iter{static_cast<int>(blockIdx.x) / 2, static_cast<int>(gridDim.x) / 2, num_m2 * num_n, num_n, rank};
+    } else {
+        const int num_m = static_cast<int>((M + kBM - 1) / kBM);
+        it = Iter{static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), num_m * num_n, num_n, BN};
+    }
 
-    const uint32_t tmem_base = pipe_setup(sm, warp, &tmap_a, &tmap_b, kEpiThreads);
+    uint32_t tmem_base;
+    if constexpr (k2Cta) tmem_base = pipe2_setup(sm, warp, &tmap_a, &tmap_b);
+    else tmem_base = pipe_setup(sm, warp, &tmap_a, &tmap_b, kEpiThreads);
 
     if (warp == 0) {
-        if (elect_one()) pipe_produce(sm, &tmap_a, &tmap_b, it, kblocks, kEvictNormal, kEvictLast);
+        if (elect_one()) {
+            if constexpr (k2Cta) pipe2_produce(sm, &tmap_a, &tmap_b, it, kblocks, rank, kEvictNormal, kEvictLast);
+            else pipe_produce(sm, &tmap_a, &tmap_b, it, kblocks, kEvictNormal, kEvictLast);
+        }
     } else if (warp == 1) {
-        if (elect_one()) pipe_mma<GemmSmem, kF16>(sm, tmem_base, it, kblocks);
+        if (elect_one()) {
+            if constexpr (k2Cta) {
+                if (rank == 0) pipe2_mma<SM, kF16>(sm, tmem_base, it, kblocks);
+            } else {
+                pipe_mma<SM, kF16>(sm, tmem_base, it, kblocks);
+            }
+        }
     } else {
         const int ew = warp - 2;         // 0..7
         const int grp = ew >> 2;         // column half owned by this warp's group
         const int lane_grp = warp & 3;   // TMEM lanes [32*lane_grp, +32) are the only ones this warp may read
         const int trow = lane_grp * 32 + lane;
         const bool leader = (ew & 3) == 0 && lane == 0;  // issues the group's TMA traffic
-        uint8_t* stage_tile = sm.pre() + grp * kStageTileBytes;
-        uint8_t* my_row = stage_tile + trow * 128;
+        // kBufs staging tiles per group. With two, chunk c of a tile uses tile c & 1: a store is
+        // still draining from one while the next chunk is written into the other, and (residual
+        // epilogue) both residual chunks of the NEXT tile are fetched before its accumulator is
+        // even complete, so neither TMA latency sits on the epilogue's critical path.
+        constexpr int kBufs = kGemmStageBufs<k2Cta>;
+        static_assert(kBufs == 1 || EPI != EPI_BIAS_RESIDUAL || CPG == 2, "residual prefetch assumes two chunks per tile");
+        uint8_t* stage_base = sm.pre() + grp * kBufs * kStageTileBytes;
         const int sw = trow & 7;
-        uint64_t* res_bar = sm.aux(grp);
-        uint32_t res_phase = 0;
+        uint32_t res_phase = 0;  // bit b = parity of the next completion of this group's residual barrier b
         if (leader) {
             tma_prefetch_desc(&tmap_c);
             if (EPI == EPI_BIAS_RESIDUAL) tma_prefetch_desc(&tmap_r);
@@ -124,6 +172,19 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         uint32_t acc_phase = 0;
         int row_a, row_b;
         while (it.next(row_a, row_b)) {
+            if (EPI == EPI_BIAS_RESIDUAL && kBufs == 2 && leader) {
+#pragma unroll
+                for (int c = 0; c < CPG; ++c) {
+                    const int col0 = row_b + grp * (BN / 2) + c * CW;
+                    if (col0 < N) {
+                        // the store that last used this tile (same chunk, previous tile) has been read
+                        if (c == 0) tma_store_wait_read<1>();
+                        else tma_store_wait_read<0>();
+                        mbar_arrive_expect_tx(sm.aux(grp * 2 + c), kStageTileBytes);
+                        tma_load_2d(&tmap_r, sm.aux(grp * 2 + c), stage_base + c * kStageTileBytes, col0, row_a, kEvictFirst);
+                    }
+                }
+            }
             mbar_wait(sm.tmem_full(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
@@ -132,7 +193,11 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             for (int c = 0; c < CPG; ++c) {
                 const int col0 = row_b + grp * (BN / 2) + c * CW;
                 const bool live = col0 < N;  // group-uniform
-                if (EPI == EPI_BIAS_RESIDUAL && live && leader) {
+                const int buf = c & (kBufs - 1);
+                uint8_t* stage_tile = stage_base + buf * kStageTileBytes;
+                uint8_t* my_row = stage_tile + trow * 128;
+                uint64_t* res_bar = sm.aux(grp * 2 + buf);
+                if (EPI == EPI_BIAS_RESIDUAL && kBufs == 1 && live && leader) {
                     tma_store_wait_read<0>();  // the previous store has drained the staging tile
                     mbar_arrive_expect_tx(res_bar, kStageTileBytes);
                     tma_load_2d(&tmap_r, res_bar, stage_tile, col0, row_a, kEvictFirst);
@@ -144,7 +209,12 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
                 tmem_ld_wait();
                 if (c == CPG - 1) {  // accumulator fully read by this thread: hand the buffer back
                     tc_fence_before();
-                    mbar_arrive(sm.tmem_empty(acc));
+                    if constexpr (k2Cta) {  // one arrival per warp on the leader CTA's barrier
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(sm.tmem_empty(acc)), 0));
+                    } else {
+                        mbar_arrive(sm.tmem_empty(acc));
+                    }
                 }
                 if (!live) continue;
                 float v[CW];
@@ -169,8 +239,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
                     for (int j = 0; j < CW; ++j) v[j] = kF16 ? gelu_erf(v[j]) : gelu_tanh_fit(v[j]);
                 }
                 if (EPI == EPI_BIAS_RESIDUAL) {
-                    mbar_wait(res_bar, res_phase);
-                    res_phase ^= 1;
+                    mbar_wait(res_bar, (res_phase >> buf) & 1u);
+                    res_phase ^= 1u << buf;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const uint4 u = *reinterpret_cast<const uint4*>(my_row + ((j ^ sw) << 4));
@@ -183,8 +253,9 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
                         }
                     }
                 } else {
-                    if (leader) tma_store_wait_read<0>();
-                    named_bar_sync(1 + grp, 128);  // staging tile is free
+                    // the store that last read this staging tile has drained
+                    if (leader) tma_store_wait_read<kBufs - 1>();
+                    named_bar_sync(1 + grp, 128);
                 }
                 if constexpr (sizeof(OutT) == 2) {
 #pragma unroll
@@ -216,7 +287,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         }
         if (leader) tma_store_wait<0>();
     }
-    pipe_teardown(sm, warp, tmem_base);
+    if constexpr (k2Cta) pipe2_teardown(sm, warp, tmem_base);
+    else pipe_teardown(sm, warp, tmem_base);
 }
 
 template <int EPI, bool kF16, typename OutT>
@@ -237,7 +309,36 @@ static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb
                   (long long)lda, (const void*)B, (long long)ldb, (const void*)C, (long long)ldc);
         return ARB_ERR_CUDA;
     }
-    auto kern = gemm16_kernel<EPI, kF16, OutT>;
+    const bool pair = g_gemm_mode == 2 || (g_gemm_mode == 0 && M > 2 * kBM * (num_sms() / 2));
+    if (pair) {
+        // clusters of two CTAs, one 256 x 256 tile per pair; B is staged in halves of 128 rows
+        if (!make_tmap_bf16_k64(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), kGemmBN / 2)) {
+            set_error("cuTensorMapEncodeTiled failed (B half tile)");
+            return ARB_ERR_CUDA;
+        }
+        auto kern = gemm16_kernel<EPI, kF16, OutT, true>;
+        constexpr int smem = Gemm2Smem::kExtraOffset + 1024;
+        static_assert(smem <= 232448, "pair GEMM shared memory exceeds 227 KB");
+        ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int64_t tiles = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kGemmBN - 1) / kGemmBN);
+        int64_t nclusters = num_sms() / 2;
+        if (nclusters > tiles) nclusters = tiles;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>(nclusters * 2));
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        ARB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tr, bias, M, N, K));
+        return ARB_OK;
+    }
+    auto kern = gemm16_kernel<EPI, kF16, OutT, false>;
     constexpr int smem = GemmSmem::kExtraOffset + 1024;  // +1024: alignment slack
     static_assert(smem <= 232448, "GEMM shared memory exceeds 227 KB");
     ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -16,17 +16,18 @@ constexpr int kBK = 64;
 
 // Shared-memory carve-up: [STAGES x (A tile | B tile)] [PRE bytes, 1024-aligned: epilogue staging]
 // [barriers] [extra...]
-template <int BN, int STAGES, int PRE = 0>
+// CTAS = 2: CTA-pair layout, each CTA stages only its half (BN / 2 rows) of the B tile.
+template <int BN, int STAGES, int PRE = 0, int CTAS = 1>
 struct PipeSmem {
     static constexpr int kBN = BN;
     static constexpr int kStages = STAGES;
     static constexpr int kABytes = kBM * kBK * 2;
-    static constexpr int kBBytes = BN * kBK * 2;
+    static constexpr int kBBytes = (BN / CTAS) * kBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kPreOffset = STAGES * kStageBytes;
     static constexpr int kBarOffset = kPreOffset + PRE;
-    // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] aux[2] + tmem base ptr
-    static constexpr int kNumBars = 2 * STAGES + 6;
+    // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] aux[4] + tmem base ptr
+    static constexpr int kNumBars = 2 * STAGES + 8;
     static constexpr int kBarBytes = kNumBars * 8 + 16;
     static constexpr int kExtraOffset = kBarOffset + ((kBarBytes + 127) / 128) * 128;
 
@@ -66,8 +67,8 @@ __device__ __forceinline__ uint32_t pipe_setup(const SM& sm, int warp, const voi
         for (int s = 0; s < 2; ++s) {
             mbar_init(sm.tmem_full(s), 1);
             mbar_init(sm.tmem_empty(s), epi_threads);
-            mbar_init(sm.aux(s), 1);
         }
+        for (int s = 0; s < 4; ++s) mbar_init(sm.aux(s), 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -144,6 +145,109 @@ __device__ __forceinline__ void pipe_mma(const SM& sm, uint32_t tmem_base, TileI
             }
         }
         umma_commit(sm.tmem_full(acc));
+        if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair. Each CTA
+// loads its own 128 rows of A and its half of the B rows; every load credits the LEADER's (rank 0)
+// full barrier, the leader issues the M = 256 MMAs, and its commits arrive on the empty /
+// tmem_full barriers of BOTH CTAs. Each CTA's epilogue drains its own 128 accumulator rows and
+// reports to the leader's tmem_empty barrier (one arrival per warp). Compared with two
+// independent CTAs this halves the B bytes staged per SM and per MMA, which buys a deeper ring.
+constexpr int kPairEpiArrivals = 2 * 8;  // 2 CTAs x 8 epilogue warps
+
+template <class SM>
+__device__ __forceinline__ uint32_t pipe2_setup(const SM& sm, int warp, const void* tmap_a, const void* tmap_b) {
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(tmap_a);
+        tma_prefetch_desc(tmap_b);
+        for (int s = 0; s < SM::kStages; ++s) {
+            mbar_init(sm.full(s), 1);
+            mbar_init(sm.empty(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(sm.tmem_full(s), 1);
+            mbar_init(sm.tmem_empty(s), kPairEpiArrivals);
+        }
+        for (int s = 0; s < 4; ++s) mbar_init(sm.aux(s), 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_2cta(sm.tmem_ptr(), tmem_cols_for<SM::kBN>());
+        tmem_relinquish_2cta();
+    }
+    tc_fence_before();
+    cluster_sync_all();  // both CTAs' barriers and TMEM exist before any cross-CTA arrive / MMA
+    tc_fence_after();
+    return *sm.tmem_ptr();
+}
+
+template <class SM>
+__device__ __forceinline__ void pipe2_teardown(const SM& sm, int warp, uint32_t tmem_base) {
+    tc_fence_before();
+    cluster_sync_all();  // the peer may still be reading operands / receiving commits until here
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc_2cta(tmem_base, tmem_cols_for<SM::kBN>());
+    }
+}
+
+// Producer (one elected lane in EACH CTA). TileIter: bool next(int& row_a, int& row_b) with
+// row_a = this CTA's first A row, row_b = first B row of the pair's tile.
+template <class SM, class TileIter>
+__device__ __forceinline__ void pipe2_produce(const SM& sm, const void* tmap_a, const void* tmap_b, TileIter it,
+                                              int kblocks, int rank, uint64_t hint_a, uint64_t hint_b) {
+    int stage = 0;
+    uint32_t phase = 0;
+    int row_a, row_b;
+    while (it.next(row_a, row_b)) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(sm.empty(stage), phase ^ 1);
+            if (rank == 0) mbar_arrive_expect_tx(sm.full(stage), 2 * SM::kStageBytes);
+            const uint32_t full_leader = map_to_cta(smem_u32(sm.full(stage)), 0);
+            tma_load_2d_2cta(tmap_a, full_leader, sm.a(stage), kb * kBK, row_a, hint_a);
+            tma_load_2d_2cta(tmap_b, full_leader, sm.b(stage), kb * kBK, row_b + rank * (SM::kBN / 2), hint_b);
+            if (++stage == SM::kStages) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+    }
+}
+
+// MMA issuer (leader CTA only): 4 x (256 x BN x 16) per K-block.
+template <class SM, bool kF16, class TileIter>
+__device__ __forceinline__ void pipe2_mma(const SM& sm, uint32_t tmem_base, TileIter it, int kblocks) {
+    constexpr uint32_t idesc = umma_idesc_16bit(2 * kBM, SM::kBN, kF16);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int row_a, row_b;
+    while (it.next(row_a, row_b)) {
+        mbar_wait_cluster(sm.tmem_empty(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * SM::kBN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(sm.full(stage), phase);
+            tc_fence_after();
+            const uint64_t da = umma_desc_sw128(smem_u32(sm.a(stage)));
+            const uint64_t db = umma_desc_sw128(smem_u32(sm.b(stage)));
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+                umma_bf16_ss_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2cta(sm.empty(stage), 0b11);
+            if (++stage == SM::kStages) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+        umma_commit_2cta(sm.tmem_full(acc), 0b11);
         if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;

@@ -222,3 +222,12 @@ class ShardedCorpusIndex:
         static_q.copy_(queries, non_blocking=True)
         g.replay()
         return res
+
+    def close(self):
+        """Drop the captured graphs and exchange buffers. Call it (on every rank) before
+        `destroy_process_group`: a live graph that holds a captured collective keeps the
+        communicator busy at teardown."""
+        if self._graphs:
+            self.index._torch.cuda.synchronize(self.index.corpus.device)
+        self._graphs.clear()
+        self._bufs.clear()

@@ -320,6 +320,8 @@ def run_b200(args):
                          "traffic": None},
             "top1_score_mean": float(fs[:, 0].mean().item()),
         }
+    if sharded is not None:
+        sharded.close()
     del index, sharded, corpus
     torch.cuda.empty_cache()
 

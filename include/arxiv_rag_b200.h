@@ -141,6 +141,10 @@ int arb_topk_search_launches(int32_t dtype);
  * callers that want to compose the encoder themselves. All pointers are device pointers;
  * `dtype` is the 16-bit activation format (ARB_DTYPE_BF16 or ARB_DTYPE_F16).
  * ------------------------------------------------------------------------------------------ */
+/* Tile schedule of the arb_gemm16* kernels (process-wide; for tests and benchmarks): 0 = auto,
+ * 1 = one CTA per 128x256 tile (tcgen05 cta_group::1), 2 = CTA pairs sharing a 256x256 tile
+ * (cta_group::2, thread-block clusters of two). Auto picks pairs for large M. */
+int arb_set_gemm_mode(int32_t mode);
 /* C[M,N] = epi(A[M,K] . B[N,K]^T + bias[N]) (+ R[M,N]); 16-bit operands, fp32 accumulate. */
 int arb_gemm16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                const float* bias, const void* R, int64_t ldr, int64_t M, int32_t N, int32_t K,

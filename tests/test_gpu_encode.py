@@ -98,6 +98,18 @@ def test_oracle_parity_baseline_shape(cuda, full_model, dtype):
     enc.close()
 
 
+def test_oracle_parity_large_batch_pair_gemm(cuda, full_model):
+    """A batch with more than 256 x (SMs / 2) tokens, where the encoder's GEMMs switch to the
+    CTA-pair schedule (tcgen05 cta_group::2): same parity bar against the fp32 oracle."""
+    arch, sd, model = full_model
+    enc = _encoder(arch, sd, "bf16", max_batch=52, max_seq=384)
+    ids, mask = eo.synthetic_tokens(52, 384, seed=77, full_length=True)
+    ref = eo.oracle_encode(model, ids, mask, batch_size=13)
+    got = enc.encode((ids, mask), batch_size=52, normalize_embeddings=True)
+    assert _cos(got, ref).min() >= COS_TOL
+    enc.close()
+
+
 def test_eps_is_a_parameter(cuda):
     """layer_norm_eps 1e-12 (installed MPNetConfig default) as well as 1e-5 (published config)."""
     arch = MPNetArch(vocab_size=1000, num_layers=2, layer_norm_eps=1e-12)

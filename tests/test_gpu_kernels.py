@@ -56,6 +56,71 @@ def test_gemm_epilogues(lib, cuda, dt, epi):
     assert _rel_err(C, ref) < tol
 
 
+@pytest.fixture
+def pair_schedule(lib):
+    """Force the CTA-pair schedule (tcgen05 cta_group::2, clusters of two CTAs per 256x256 tile);
+    auto only picks it for M > 256 * (SMs / 2)."""
+    _lib.check(lib.arb_set_gemm_mode(2))
+    yield
+    _lib.check(lib.arb_set_gemm_mode(0))
+
+
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+@pytest.mark.parametrize("shape", [(256, 256, 64), (128, 256, 128), (300, 512, 768), (4099, 2304, 768), (513, 768, 3072),
+                                   (1, 32, 8), (777, 264, 200), (40000, 3072, 64)])
+def test_gemm_pair_schedule_mainloop(lib, cuda, pair_schedule, dt, shape):
+    """Same bar as test_gemm_mainloop_fp32_out through the CTA-pair kernel: ragged M (the second
+    CTA's rows past the end), N not a multiple of the half tile, K tail, more tiles than pairs."""
+    M, N, K = shape
+    tdt, code, _ = DT[dt]
+    torch.manual_seed(0)
+    A = (torch.randn(M, K, device=cuda) * 0.5).to(tdt)
+    B = (torch.randn(N, K, device=cuda) * 0.5).to(tdt)
+    C = torch.full((M, N), float("nan"), device=cuda)
+    _lib.check(lib.arb_gemm16_f32out(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, M, N, K, code, _stream()))
+    assert _rel_err(C, A.float() @ B.float().T) < 2e-5
+
+
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+@pytest.mark.parametrize("epi", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(1777, 768, 768), (40000, 264, 128)])
+def test_gemm_pair_schedule_epilogues(lib, cuda, pair_schedule, dt, epi, shape):
+    """Epilogues of the CTA-pair kernel (double-buffered staging, residual chunks prefetched a tile
+    ahead); N = 264 leaves staging chunks unused in the last column block."""
+    tdt, code, tol = DT[dt]
+    torch.manual_seed(1)
+    M, N, K = shape
+    A = (torch.randn(M, K, device=cuda) * 0.3).to(tdt)
+    B = (torch.randn(N, K, device=cuda) * 0.05).to(tdt)
+    bias = torch.randn(N, device=cuda)
+    R = torch.randn(M, N, device=cuda).to(tdt)
+    ref = A.float() @ B.float().T + bias
+    ref = [ref, torch.nn.functional.gelu(ref), ref + R.float()][epi]
+    C = torch.zeros(M, N, device=cuda, dtype=tdt)
+    _lib.check(lib.arb_gemm16(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, bias.data_ptr(),
+                              R.data_ptr() if epi == 2 else 0, N, M, N, K, epi, code, _stream()))
+    assert _rel_err(C, ref) < tol
+
+
+def test_gemm_schedules_agree_bitwise(lib, cuda):
+    """Both schedules accumulate each output element over K in the same order, so they must agree
+    bit for bit — the encoder's result does not depend on which one `auto` picks."""
+    torch.manual_seed(2)
+    M, N, K = 3000, 768, 768
+    A = (torch.randn(M, K, device=cuda) * 0.3).to(torch.bfloat16)
+    B = (torch.randn(N, K, device=cuda) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device=cuda)
+    out = []
+    for mode in (1, 2):
+        _lib.check(lib.arb_set_gemm_mode(mode))
+        C = torch.zeros(M, N, device=cuda, dtype=torch.bfloat16)
+        _lib.check(lib.arb_gemm16(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, bias.data_ptr(), 0, N, M, N, K, 1,
+                                  _lib.ARB_DTYPE_BF16, _stream()))
+        out.append(C)
+    _lib.check(lib.arb_set_gemm_mode(0))
+    assert torch.equal(out[0], out[1])
+
+
 @pytest.mark.parametrize("dt", ["bf16", "fp16"])
 @pytest.mark.parametrize("shape", [(128, 768, 768), (1000, 768, 3072), (333, 256, 128), (5000, 1024, 768)])
 def test_gemm_residual_layernorm_cluster(lib, cuda, dt, shape):

@@ -336,6 +336,55 @@ def stage_perf():
     return True
 
 
+def stage_gemm2():
+    """CTA-pair GEMM (cta_group::2): parity against torch for every epilogue incl. ragged edges,
+    then the encoder's four shapes timed in both schedules."""
+    ok = True
+    torch.manual_seed(3)
+    _lib.check(lib().arb_set_gemm_mode(2))
+    for d in ("bf16", "fp16"):
+        for (M, N, K) in [(256, 256, 64), (256, 256, 768), (128, 256, 128), (300, 512, 768), (1000, 768, 768), (4099, 2304, 768),
+                          (513, 768, 3072), (40000, 3072, 768), (777, 264, 64)]:
+            A = (torch.randn(M, K, device=DEV) * 0.5).to(tdtype(d))
+            B = (torch.randn(N, K, device=DEV) * 0.5).to(tdtype(d))
+            C = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
+            _lib.check(lib().arb_gemm16_f32out(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, M, N, K, dcode(d), stream()))
+            torch.cuda.synchronize()
+            ok &= report(f"pair gemm_f32out {d} M{M} N{N} K{K}", C, A.float() @ B.float().T, 2e-5)
+        for (M, N, K) in [(1777, 768, 768), (40000, 264, 128), (70000, 3072, 64)]:
+            A = (torch.randn(M, K, device=DEV) * 0.3).to(tdtype(d))
+            B = (torch.randn(N, K, device=DEV) * 0.05).to(tdtype(d))
+            bias = torch.randn(N, device=DEV)
+            R = torch.randn(M, N, device=DEV).to(tdtype(d))
+            base = A.float() @ B.float().T + bias
+            for epi, name, ref in [(0, "bias", base), (1, "bias_gelu", torch.nn.functional.gelu(base)), (2, "bias_residual", base + R.float())]:
+                C = torch.zeros(M, N, device=DEV, dtype=tdtype(d))
+                _lib.check(lib().arb_gemm16(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, bias.data_ptr(),
+                                            R.data_ptr() if epi == 2 else 0, N, M, N, K, epi, dcode(d), stream()))
+                torch.cuda.synchronize()
+                ok &= report(f"pair gemm_{name} {d} M{M} N{N} K{K}", C, ref, 6e-3 if d == "bf16" else 8e-4)
+            del A, B, R, base
+    M = 1024 * 384
+    for (N, K, epi) in [(2304, 768, 0), (768, 768, 2), (3072, 768, 1), (768, 3072, 2)]:
+        A = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+        B = (torch.randn(N, K, device=DEV) * 0.05).to(torch.bfloat16)
+        C = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+        R = torch.randn(M, N, device=DEV).to(torch.bfloat16) if epi == 2 else None
+        bias = torch.randn(N, device=DEV)
+        res = []
+        for mode in (1, 2):
+            _lib.check(lib().arb_set_gemm_mode(mode))
+            ms = _time(lambda: _lib.check(lib().arb_gemm16(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, bias.data_ptr(),
+                                                           R.data_ptr() if R is not None else 0, N, M, N, K, epi, _lib.ARB_DTYPE_BF16, stream())),
+                       iters=10, warm=3)
+            res.append(ms)
+        fl = 2.0 * M * N * K
+        print(f"gemm M{M} N{N} K{K} epi{epi}: single {res[0]:.3f} ms {fl / res[0] / 1e9:.1f} TF | pair {res[1]:.3f} ms {fl / res[1] / 1e9:.1f} TF", flush=True)
+        del A, B, C, R
+    _lib.check(lib().arb_set_gemm_mode(0))
+    return ok
+
+
 def stage_searchperf():
     """Search only: small-shard / small-Q (HBM-bound, the 8-GPU regime) and large-k cases, plus a
     per-kernel breakdown of one call from the CUPTI activity records (torch.profiler)."""
@@ -367,7 +416,7 @@ def stage_searchperf():
     return True
 
 
-STAGES = {"searchperf": stage_searchperf, "gemm": stage_gemm, "gemmln": stage_gemmln, "rowops": stage_rowops, "attention": stage_attention, "search": stage_search,
+STAGES = {"gemm2": stage_gemm2, "searchperf": stage_searchperf, "gemm": stage_gemm, "gemmln": stage_gemmln, "rowops": stage_rowops, "attention": stage_attention, "search": stage_search,
           "encode": stage_encode, "perf": stage_perf}
 
 if __name__ == "__main__":
