@@ -81,6 +81,13 @@ SIGNATURES = {
     "arb_topk_merge": (C.c_int, [_VP, _VP, _I32, _I64, _I32, _VP, _VP, _VP]),
     "arb_topk_search_launches": (C.c_int, [_I32]),
     "arb_set_gemm_mode": (C.c_int, [_I32]),
+    "arb_topk_exchange_bytes": (_SZ, [_I32, _SZ]),
+    "arb_exchange_alloc": (C.c_int, [_SZ, C.POINTER(C.c_void_p)]),
+    "arb_exchange_free": (C.c_int, [_VP]),
+    "arb_ipc_export": (C.c_int, [_VP, _VP]),
+    "arb_ipc_import": (C.c_int, [_VP, C.POINTER(C.c_void_p)]),
+    "arb_ipc_close": (C.c_int, [_VP]),
+    "arb_topk_exchange_merge": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _I32, _SZ, _VP, _VP, _VP]),
     "arb_topk_record_bytes": (_SZ, [_I64, _I32]),
     "arb_topk_record_ids_offset": (_SZ, [_I64, _I32]),
     "arb_topk_merge_records": (C.c_int, [_VP, _I32, _I64, _I32, _VP, _VP, _VP]),

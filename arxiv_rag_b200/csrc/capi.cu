@@ -8,6 +8,8 @@
 #include <vector>
 
 #include "../../include/arxiv_rag_b200.h"
+#include <cstring>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -306,6 +308,53 @@ int arb_topk_merge(const float* scores_dev, const int64_t* ids_dev, int32_t G, i
                    float* out_scores_dev, int64_t* out_ids_dev, void* stream) {
     return launch_topk_merge(scores_dev, ids_dev, G, Q, k, out_scores_dev, out_ids_dev,
                              static_cast<cudaStream_t>(stream));
+}
+
+size_t arb_topk_exchange_bytes(int32_t G, size_t slot_bytes) { return G > 0 ? topk_exchange_bytes(G, slot_bytes) : 0; }
+
+int arb_exchange_alloc(size_t bytes, void** dev_ptr_out) {
+    ARB_REQUIRE(dev_ptr_out != nullptr && bytes > 0, "exchange_alloc: bad arguments");
+    void* p = nullptr;
+    ARB_CHECK_CUDA(cudaMalloc(&p, bytes));  // a whole allocation of its own: its IPC handle maps exactly this buffer
+    ARB_CHECK_CUDA(cudaMemset(p, 0, bytes));
+    ARB_CHECK_CUDA(cudaDeviceSynchronize());
+    *dev_ptr_out = p;
+    return ARB_OK;
+}
+
+int arb_exchange_free(void* dev_ptr) {
+    if (dev_ptr) ARB_CHECK_CUDA(cudaFree(dev_ptr));
+    return ARB_OK;
+}
+
+int arb_ipc_export(const void* dev_ptr, void* handle_out_64) {
+    ARB_REQUIRE(dev_ptr && handle_out_64, "ipc_export: null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    ARB_CHECK_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+    memcpy(handle_out_64, &h, sizeof(h));
+    return ARB_OK;
+}
+
+int arb_ipc_import(const void* handle_64, void** dev_ptr_out) {
+    ARB_REQUIRE(handle_64 && dev_ptr_out, "ipc_import: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_64, sizeof(h));
+    void* p = nullptr;
+    ARB_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr_out = p;
+    return ARB_OK;
+}
+
+int arb_ipc_close(void* dev_ptr) {
+    if (dev_ptr) ARB_CHECK_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return ARB_OK;
+}
+
+int arb_topk_exchange_merge(const void* local_record_dev, const void* peer_bufs_dev, int32_t rank, int32_t G, int64_t Q,
+                            int32_t k, size_t slot_bytes, float* out_scores_dev, int64_t* out_ids_dev, void* stream) {
+    return launch_topk_exchange_merge(local_record_dev, static_cast<void* const*>(peer_bufs_dev), rank, G, Q, k,
+                                      slot_bytes, out_scores_dev, out_ids_dev, static_cast<cudaStream_t>(stream));
 }
 
 int arb_set_gemm_mode(int32_t mode) {

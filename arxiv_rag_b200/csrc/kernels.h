@@ -75,5 +75,9 @@ size_t topk_record_ids_offset(int64_t Q, int k);
 size_t topk_record_bytes(int64_t Q, int k);
 int launch_topk_merge_records(const void* records, int G, int64_t Q, int k, float* out_scores,
                               int64_t* out_ids, cudaStream_t stream);
+// Peer-memory exchange (one kernel: push records to all ranks' mapped buffers, flag, wait, merge).
+size_t topk_exchange_bytes(int G, size_t slot_bytes);
+int launch_topk_exchange_merge(const void* local_record, void* const* peer_bufs_dev, int rank, int G, int64_t Q,
+                               int k, size_t slot_bytes, float* out_scores, int64_t* out_ids, cudaStream_t stream);
 
 }  // namespace arb

@@ -32,13 +32,17 @@ struct SearchPlan {
     int grid;
 };
 
-static SearchPlan make_plan(int64_t Q, int64_t N) {
+static SearchPlan make_plan(int64_t Q, int64_t N, int k) {
     SearchPlan p;
     p.nq = static_cast<int>((Q + kBM - 1) / kBM);
     p.nchunks = static_cast<int>((N + kSBN - 1) / kSBN);
     const int G = num_sms();
-    // Pick the split count that wastes the fewest CTA-rounds; prefer fewer splits on ties
-    // (less merge work). Keep at least 4 chunks per split when the corpus allows it.
+    // Every item (split x query tile) starts with empty lists and pays a warm-up while its k-th
+    // best is still low: ~k (1 + ln(rows/k)) survivors per query row have to be merged, which for
+    // the shared-memory lists (k > 16) costs about 1.4 k chunk-times of epilogue work per item,
+    // for the register lists a few chunks. time ~ rounds * (cps + warm); ideal ~ nq * nchunks / G.
+    // Pick the split count with the best ratio; prefer fewer splits on near-ties (less merge work).
+    const double warm = k > 16 ? 1.4 * k : 3.0;
     int best = 1;
     double best_eff = -1.0;
     const int max_split = p.nchunks < 4 ? 1 : (p.nchunks / 4 < 4 * G ? p.nchunks / 4 : 4 * G);
@@ -48,13 +52,12 @@ static SearchPlan make_plan(int64_t Q, int64_t N) {
         if (s_eff != s) continue;
         const int64_t items = static_cast<int64_t>(p.nq) * s;
         const int64_t rounds = (items + G - 1) / G;
-        // time ~ rounds * cps ; ideal ~ nq * nchunks / G
-        const double eff = (static_cast<double>(p.nq) * p.nchunks / G) / (static_cast<double>(rounds) * cps);
+        const double eff = (static_cast<double>(p.nq) * p.nchunks / G) / (static_cast<double>(rounds) * (cps + warm));
         if (eff > best_eff + 0.02) {
             best_eff = eff;
             best = s;
         }
-        if (items >= 16ll * G && eff > 0.97) break;
+        if (items >= 16ll * G) break;
     }
     p.nsplit = best;
     p.cps = (p.nchunks + best - 1) / best;
@@ -373,14 +376,14 @@ __device__ __forceinline__ bool sorts_ahead(float sa, IdT ia, float sb, IdT ib) 
     return sa > sb || (sa == sb && ia < ib);
 }
 
+// Merge the G lists of query q; called by all kMergeThreads threads of a block. Ends without a
+// barrier: a caller that loops over queries must __syncthreads() between calls.
 template <typename IdT>
-__global__ void __launch_bounds__(kMergeThreads)
-topk_tree_merge_kernel(const float* __restrict__ scores, const IdT* __restrict__ ids, int G, int64_t stride_s,
-                       int64_t stride_i, int64_t Q, int k, int64_t id_offset, float* __restrict__ out_scores,
-                       int64_t* __restrict__ out_ids) {
-    extern __shared__ __align__(16) uint8_t s_merge[];
+__device__ __forceinline__ void merge_one_query(uint8_t* s_merge, const float* __restrict__ scores,
+                                                const IdT* __restrict__ ids, int G, int64_t stride_s, int64_t stride_i,
+                                                int64_t q, int k, int64_t id_offset, float* __restrict__ out_scores,
+                                                int64_t* __restrict__ out_ids) {
     const int tid = threadIdx.x;
-    const int64_t q = blockIdx.x;
     const int n = G * k, half = ((G + 1) / 2) * k;
     // buffers: ids A[n], ids B[half], scores A[n], scores B[half], list lengths A[G], B[(G+1)/2]
     IdT* idA = reinterpret_cast<IdT*>(s_merge);
@@ -555,6 +558,93 @@ topk_tree_merge_kernel(const float* __restrict__ scores, const IdT* __restrict__
     }
 }
 
+template <typename IdT>
+__global__ void __launch_bounds__(kMergeThreads)
+topk_tree_merge_kernel(const float* __restrict__ scores, const IdT* __restrict__ ids, int G, int64_t stride_s,
+                       int64_t stride_i, int64_t Q, int k, int64_t id_offset, float* __restrict__ out_scores,
+                       int64_t* __restrict__ out_ids) {
+    extern __shared__ __align__(16) uint8_t s_merge[];
+    merge_one_query<IdT>(s_merge, scores, ids, G, stride_s, stride_i, static_cast<int64_t>(blockIdx.x), k, id_offset,
+                         out_scores, out_ids);
+}
+
+// ----------------------------------------------------------------------------- peer-memory exchange + merge
+// The multi-GPU exchange step as ONE kernel per rank instead of an all-gather followed by a merge:
+// every rank owns an exchange buffer that its peers have mapped (CUDA IPC over NVLink/NVSwitch):
+//   [header: flags[2][16], done, epoch] [parity 0: G slots] [parity 1: G slots]
+// The kernel (a) stores this rank's record into slot[rank] of EVERY rank's buffer with plain
+// peer stores, (b) its last block to finish publishes flags[parity][rank] = epoch in every buffer
+// (release, system scope), (c) every block waits until all G flags of its own buffer show the
+// epoch (acquire), (d) the blocks merge the G records where they landed. The epoch lives in the
+// buffer and advances by one per launch, so a captured CUDA graph replays correctly; slots are
+// double-buffered by epoch parity, and a rank cannot run two epochs ahead of a peer because it
+// needs that peer's flag of the epoch in between.
+constexpr int kExchMaxRanks = 16;
+constexpr size_t kExchHeaderBytes = 1024;
+struct ExchangeHeader {
+    uint32_t flags[2][kExchMaxRanks];
+    uint32_t done;
+    uint32_t epoch;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kMergeThreads)
+topk_exchange_merge_kernel(const uint8_t* __restrict__ local_record, uint8_t* const* __restrict__ peer_bufs, int rank,
+                           int G, int64_t Q, int k, size_t rec_bytes, size_t ids_off, size_t slot_bytes,
+                           float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+    extern __shared__ __align__(16) uint8_t s_merge[];
+    const int tid = threadIdx.x;
+    uint8_t* mine_raw = peer_bufs[rank];
+    ExchangeHeader* mine = reinterpret_cast<ExchangeHeader*>(mine_raw);
+    const uint32_t epoch = ld_acquire_sys(&mine->epoch) + 1u;  // advanced by the last block below
+    const size_t parity = epoch & 1u;
+    // (a) push the record to every rank (own buffer included)
+    const size_t words = rec_bytes / 8;
+    const uint2* src = reinterpret_cast<const uint2*>(local_record);
+    for (int p = 0; p < G; ++p) {
+        uint2* dst = reinterpret_cast<uint2*>(peer_bufs[p] + kExchHeaderBytes + (parity * G + rank) * slot_bytes);
+        for (size_t i = static_cast<size_t>(blockIdx.x) * kMergeThreads + tid; i < words;
+             i += static_cast<size_t>(gridDim.x) * kMergeThreads)
+            dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    // (b) last block of this rank: advance the epoch, raise this rank's flag everywhere
+    if (tid == 0) {
+        const uint32_t prev = atomicAdd(&mine->done, 1u);
+        if (prev == gridDim.x - 1) {
+            mine->done = 0;
+            mine->epoch = epoch;
+            __threadfence_system();
+            for (int p = 0; p < G; ++p)
+                st_release_sys(&reinterpret_cast<ExchangeHeader*>(peer_bufs[p])->flags[parity][rank], epoch);
+        }
+    }
+    // (c) all records of this epoch have landed in my buffer
+    if (tid < G) {
+        while (ld_acquire_sys(&mine->flags[parity][tid]) != epoch) {
+        }
+    }
+    __syncthreads();
+    // (d) merge them
+    const uint8_t* base = mine_raw + kExchHeaderBytes + parity * G * slot_bytes;
+    for (int64_t q = blockIdx.x; q < Q; q += gridDim.x) {
+        merge_one_query<int64_t>(s_merge, reinterpret_cast<const float*>(base),
+                                 reinterpret_cast<const int64_t*>(base + ids_off), G,
+                                 static_cast<int64_t>(slot_bytes / 4), static_cast<int64_t>(slot_bytes / 8), q, k, 0,
+                                 out_scores, out_ids);
+        __syncthreads();
+    }
+}
+
 // Fallback when G*k entries do not fit in shared memory: one warp per query, lane l owns lists
 // l, l+32, ... and offers the best of their heads each round; a warp arg-max picks the winner.
 template <typename IdT>
@@ -657,13 +747,42 @@ int launch_topk_merge_records(const void* records, int G, int64_t Q, int k, floa
                                       out_ids, stream);
 }
 
+size_t topk_exchange_bytes(int G, size_t slot_bytes) { return kExchHeaderBytes + 2 * static_cast<size_t>(G) * slot_bytes; }
+
+int launch_topk_exchange_merge(const void* local_record, void* const* peer_bufs_dev, int rank, int G, int64_t Q,
+                               int k, size_t slot_bytes, float* out_scores, int64_t* out_ids, cudaStream_t stream) {
+    ARB_REQUIRE(local_record && peer_bufs_dev && out_scores && out_ids, "topk_exchange_merge: null pointer");
+    ARB_REQUIRE(G > 1 && G <= kExchMaxRanks && rank >= 0 && rank < G, "topk_exchange_merge: bad rank %d of %d", rank, G);
+    ARB_REQUIRE(Q > 0 && k > 0, "topk_exchange_merge: bad shape Q=%lld k=%d", (long long)Q, k);
+    const size_t rec = topk_record_bytes(Q, k);
+    ARB_REQUIRE(slot_bytes % 8 == 0 && rec <= slot_bytes, "topk_exchange_merge: record (%zu B) exceeds the slot (%zu B)", rec,
+                slot_bytes);
+    ARB_REQUIRE((reinterpret_cast<uintptr_t>(local_record) & 7) == 0, "topk_exchange_merge: record must be 8-byte aligned");
+    const size_t n = static_cast<size_t>(G) * k, half = static_cast<size_t>((G + 1) / 2) * k;
+    const size_t smem = (n + half) * (8 + 4) + (static_cast<size_t>(G) * 2 + (G + 1) / 2 + 1) * 4;
+    if (smem > 200 * 1024) {
+        set_error("topk_exchange_merge: G*k = %zu entries do not fit in shared memory", n);
+        return ARB_ERR_UNSUPPORTED;
+    }
+    auto kern = topk_exchange_merge_kernel;
+    if (smem > 48 * 1024)
+        ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    // every block spins on the flags, so all of them must be resident at once: at most one per SM
+    const int grid = static_cast<int>(Q < num_sms() ? Q : num_sms());
+    kern<<<grid, kMergeThreads, smem, stream>>>(static_cast<const uint8_t*>(local_record),
+                                                reinterpret_cast<uint8_t* const*>(peer_bufs_dev), rank, G, Q, k, rec,
+                                                topk_record_ids_offset(Q, k), slot_bytes, out_scores, out_ids);
+    ARB_CHECK_CUDA(cudaGetLastError());
+    return ARB_OK;
+}
+
 // ----------------------------------------------------------------------------- bf16 search
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 size_t search_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
     (void)D;
     if (Q <= 0 || N <= 0 || k <= 0) return 0;
-    const SearchPlan p = make_plan(Q, N);
+    const SearchPlan p = make_plan(Q, N, k);
     const size_t per = static_cast<size_t>(p.nsplit) * Q * k;
     return align_up(per * 4, 256) + align_up(per * 4, 256);
 }
@@ -683,7 +802,7 @@ int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int6
         set_error("search: workspace too small (%zu < %zu bytes)", ws_bytes, need);
         return ARB_ERR_WORKSPACE;
     }
-    const SearchPlan p = make_plan(Q, N);
+    const SearchPlan p = make_plan(Q, N, k);
     const size_t per = static_cast<size_t>(p.nsplit) * Q * k;
     float* part_scores = reinterpret_cast<float*>(workspace);
     int32_t* part_ids = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) + align_up(per * 4, 256));

@@ -12,6 +12,8 @@ NCCL/NVLink and merged by the k-way merge kernel (`arb_topk_merge`).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import _lib
@@ -132,13 +134,19 @@ class ShardedCorpusIndex:
 
     Every rank holds rows `shard_bounds(N, world, rank)` and the full query batch; `search`
     returns the identical global top-k on every rank: local fused top-k written as one record
-    (`[Q,k]` float32 scores + int64 ids in a single buffer) -> ONE all_gather of the records ->
-    k-way merge of the records where they landed. The only collective on the path is that
-    all_gather. `search_graphed` replays the same three steps (search, all_gather, merge) from a
-    CUDA graph per (Q, k), for the latency-bound small-batch regime.
+    (`[Q,k]` float32 scores + int64 ids in a single buffer) -> exchange -> k-way merge.
+
+    Exchange, ranks of one node (the 8xB200 NVSwitch box): ONE kernel per rank stores the record
+    into every peer's exchange buffer (mapped through CUDA IPC), raises a flag, waits for the G
+    records of the round and merges them (`arb_topk_exchange_merge`) — no library collective on
+    the path. Records larger than a slot (`peer_slot_bytes`), ranks on different hosts, or
+    `peer_exchange=False`: one NCCL all_gather of the records + `arb_topk_merge_records`.
+    `search_graphed` replays search + exchange + merge from a CUDA graph per (Q, k), for the
+    latency-bound small-batch regime.
     """
 
-    def __init__(self, local_corpus, global_rows: int, group=None, device: int | None = None):
+    def __init__(self, local_corpus, global_rows: int, group=None, device: int | None = None,
+                 peer_exchange: bool | None = None, peer_slot_bytes: int = 1 << 20):
         import torch.distributed as dist
 
         self._dist = dist
@@ -152,6 +160,65 @@ class ShardedCorpusIndex:
         self.index = CorpusIndex(local_corpus, id_offset=lo, device=device)
         self._bufs = {}    # (Q, k) -> (local record, gathered records, out scores, out ids)
         self._graphs = {}  # (Q, k) -> (graph, static queries)
+        self._exch = None  # (own buffer address, imported peer addresses, device array of the G addresses)
+        self.peer_slot_bytes = int(peer_slot_bytes) // 8 * 8
+        if peer_exchange is None:
+            peer_exchange = os.environ.get("ARB_PEER_EXCHANGE", "1") != "0"
+        if self.world > 1 and peer_exchange:
+            self._setup_peer_exchange()
+
+    def _setup_peer_exchange(self):
+        """Allocate this rank's exchange buffer, swap IPC handles, map the peers' buffers. Every
+        rank must end up with the same decision, so failures are agreed on with an all_reduce."""
+        import ctypes
+        import socket
+
+        torch = self.index._torch
+        dist = self._dist
+        lib = _lib.lib()
+        dev = self.index.corpus.device
+        ok, own, handle = True, ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(dev):
+            try:
+                if self.world > 16:
+                    raise RuntimeError("more than 16 ranks")
+                nbytes = int(lib.arb_topk_exchange_bytes(self.world, self.peer_slot_bytes))
+                _lib.check(lib.arb_exchange_alloc(nbytes, ctypes.byref(own)))
+                _lib.check(lib.arb_ipc_export(own, handle))
+            except Exception:  # noqa: BLE001 - any failure means "use the all_gather path"
+                ok = False
+            infos = [None] * self.world
+            dist.all_gather_object(infos, (socket.gethostname(), bytes(handle), ok), group=self.group)
+            ok = ok and all(i[2] for i in infos) and len({i[0] for i in infos}) == 1
+            peers, addrs = [], []
+            if ok:
+                for r, (_, h, _) in enumerate(infos):
+                    if r == self.rank:
+                        addrs.append(own.value)
+                        continue
+                    p = ctypes.c_void_p()
+                    try:
+                        _lib.check(lib.arb_ipc_import((ctypes.c_ubyte * 64).from_buffer_copy(h), ctypes.byref(p)))
+                    except Exception:  # noqa: BLE001
+                        ok = False
+                        break
+                    peers.append(p.value)
+                    addrs.append(p.value)
+            flag = torch.tensor([1 if ok else 0], device=dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 1:
+                table = torch.tensor(addrs, dtype=torch.int64).to(dev)
+                self._exch = (own.value, peers, table)
+            else:
+                for p in peers:
+                    lib.arb_ipc_close(p)
+                if own.value:
+                    lib.arb_exchange_free(own)
+            dist.barrier(group=self.group)
+
+    @property
+    def exchange(self) -> str:
+        return "peer-memory kernel (CUDA IPC over NVLink)" if self._exch is not None else "nccl all_gather"
 
     def _buffers(self, Q: int, k: int):
         torch = self.index._torch
@@ -173,6 +240,12 @@ class ShardedCorpusIndex:
         ls = local[:Q * k * 4].view(torch.float32).view(Q, k)
         li = local[ids_off:ids_off + Q * k * 8].view(torch.int64).view(Q, k)
         self.index.search(queries, k, out_scores=ls, out_ids=li)
+        if self._exch is not None and local.numel() <= self.peer_slot_bytes:
+            with torch.cuda.device(local.device):
+                _lib.check(_lib.lib().arb_topk_exchange_merge(_lib.ptr(local), _lib.ptr(self._exch[2]), self.rank, self.world,
+                                                              Q, k, self.peer_slot_bytes, _lib.ptr(out_s), _lib.ptr(out_i),
+                                                              _lib.current_stream()))
+            return out_s, out_i
         self._dist.all_gather_into_tensor(gathered, local, group=self.group)
         with torch.cuda.device(gathered.device):
             _lib.check(_lib.lib().arb_topk_merge_records(_lib.ptr(gathered), self.world, Q, k, _lib.ptr(out_s),
@@ -227,7 +300,15 @@ class ShardedCorpusIndex:
         """Drop the captured graphs and exchange buffers. Call it (on every rank) before
         `destroy_process_group`: a live graph that holds a captured collective keeps the
         communicator busy at teardown."""
-        if self._graphs:
-            self.index._torch.cuda.synchronize(self.index.corpus.device)
+        torch = self.index._torch
+        torch.cuda.synchronize(self.index.corpus.device)
         self._graphs.clear()
         self._bufs.clear()
+        if self._exch is not None:
+            own, peers, _ = self._exch
+            self._exch = None
+            self._dist.barrier(group=self.group)  # nobody is still storing into a buffer about to go away
+            with torch.cuda.device(self.index.corpus.device):
+                for p in peers:
+                    _lib.lib().arb_ipc_close(p)
+                _lib.lib().arb_exchange_free(own)

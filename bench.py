@@ -292,7 +292,7 @@ def run_b200(args):
 
     for label, Q in (("large_batch", SEARCH_Q), ("small_batch", SEARCH_Q_SMALL)):
         q = torch.nn.functional.normalize(torch.randn(Q, SEARCH_D, device=dev, generator=gq), dim=1).to(torch.bfloat16)
-        graphed = sharded is not None and Q <= 256  # latency-bound regime: replay search+all_gather+merge from a CUDA graph
+        graphed = sharded is not None and Q <= 256  # latency-bound regime: replay search + exchange + merge from a CUDA graph
         if sharded is None:
             step = lambda: index.search(q, SEARCH_K)
         elif graphed:
@@ -311,7 +311,7 @@ def run_b200(args):
         search[label] = {
             "metric": f"queries/sec exact top-{SEARCH_K} @ {SEARCH_N}x{SEARCH_D} bf16", "Q": Q, "value": Q / (ms / 1e3),
             "unit": "queries/s", "ms_per_batch": ms, "local_ms_per_batch": local_ms,
-            "path": ("cuda graph: " if graphed else "") + ("local search -> 1 all_gather of [Q,k] records -> merge" if sharded is not None else "local search"),
+            "path": ("cuda graph: " if graphed else "") + (f"local search -> [Q,k] records exchanged + merged by {sharded.exchange}" if sharded is not None else "local search"),
             "roofline": {"bound": bound,
                          "achieved": (shard_bytes / ms / 1e6) if bound == "hbm" else (flops / ms / 1e9),
                          "peak": pk["hbm_gbs"] if bound == "hbm" else pk["bf16_tflops_sustained"],

@@ -130,6 +130,22 @@ size_t arb_topk_record_bytes(int64_t Q, int32_t k);
 size_t arb_topk_record_ids_offset(int64_t Q, int32_t k);
 int arb_topk_merge_records(const void* records_dev, int32_t G, int64_t Q, int32_t k, float* out_scores_dev,
                            int64_t* out_ids_dev, void* stream);
+/* Peer-memory exchange for ranks of one node (NVLink / NVSwitch), replacing all-gather + merge by ONE
+ * kernel per rank. Each rank allocates an exchange buffer (arb_exchange_alloc, zero-filled, a CUDA
+ * allocation of its own), exports its IPC handle (64 bytes), imports its peers' and uploads the G
+ * buffer addresses (its own at index `rank`) as a device array of pointers. arb_topk_exchange_merge
+ * — called collectively, in the same order, by every rank — stores the local record into every
+ * rank's buffer, signals, waits for the G records of this round and merges them (same order rule as
+ * arb_topk_merge). slot_bytes (multiple of 8) is the per-record capacity the buffers were sized with
+ * (arb_topk_exchange_bytes); records larger than a slot must take the all-gather path. */
+size_t arb_topk_exchange_bytes(int32_t G, size_t slot_bytes);
+int arb_exchange_alloc(size_t bytes, void** dev_ptr_out);
+int arb_exchange_free(void* dev_ptr);
+int arb_ipc_export(const void* dev_ptr, void* handle_out_64);
+int arb_ipc_import(const void* handle_64, void** dev_ptr_out);
+int arb_ipc_close(void* dev_ptr);
+int arb_topk_exchange_merge(const void* local_record_dev, const void* peer_bufs_dev, int32_t rank, int32_t G, int64_t Q,
+                            int32_t k, size_t slot_bytes, float* out_scores_dev, int64_t* out_ids_dev, void* stream);
 /* out[i] = cos(emb[i], emb[i-1]) for fp32 rows [n, D] (out[0] = 1): the adjacent-sentence similarity
  * TextChunker._chunk_semantic computes with _cosine_similarity (text_processor.py:1547-1561, :1601-1605). */
 int arb_adjacent_cosine(const float* emb_dev, int64_t n, int32_t D, float* out_dev, void* stream);

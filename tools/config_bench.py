@@ -4,7 +4,7 @@
     torchrun --nproc-per-node N tools/config_bench.py cfg3   # 100k queries x 5M x 768 bf16, top-100, N GPUs
 
 cfg3 shards the corpus row-wise (ShardedCorpusIndex: local fused top-100 -> one all-gather of the
-[Q,k] records -> merge) and feeds the 100k queries in batches of --batch (default 8192). Inputs are
+[Q,k] records -> exchange -> merge) and feeds the 100k queries in batches of --batch (default 32768). Inputs are
 resident; timed with CUDA events, max over ranks. The roofline denominator is
 max(bytes/HBM peak, flops/sustained bf16 peak) with MEASURED_PEAKS.json numbers.
 """
@@ -34,7 +34,7 @@ def unit_rows(n, dev, seed, dtype):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("config", choices=["cfg2", "cfg3"])
-    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--batch", type=int, default=32768)
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -98,6 +98,8 @@ def main():
             "bound": "tensor", "batch": args.batch if args.config == "cfg3" else Q,
             "top1_mean": float(s[:, 0].mean().item())}), flush=True)
     if world > 1:
+        if hasattr(index, "close"):
+            index.close()
         dist.destroy_process_group()
 
 
