@@ -592,8 +592,8 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 __global__ void __launch_bounds__(kMergeThreads)
@@ -623,9 +623,9 @@ topk_exchange_merge_kernel(const uint8_t* __restrict__ local_record, uint8_t* co
         if (prev == gridDim.x - 1) {
             mine->done = 0;
             mine->epoch = epoch;
-            __threadfence_system();
+            __threadfence_system();  // one release fence for all G flag stores (G releases would pay G round trips)
             for (int p = 0; p < G; ++p)
-                st_release_sys(&reinterpret_cast<ExchangeHeader*>(peer_bufs[p])->flags[parity][rank], epoch);
+                st_relaxed_sys(&reinterpret_cast<ExchangeHeader*>(peer_bufs[p])->flags[parity][rank], epoch);
         }
     }
     // (c) all records of this epoch have landed in my buffer
