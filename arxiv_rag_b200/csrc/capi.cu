@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/arxiv_rag_b200.h"
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -48,6 +49,8 @@ struct LayerDev {
     h16 *w_qkv, *w_o, *w_in, *w_out;  // [3H,H] [H,H] [I,H] [H,I]
     float *b_qkv, *b_o, *b_in, *b_out;
     float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    // folded-LayerNorm path: column sums of the gamma-scaled weights (w_qkv of layers >= 1, w_in)
+    float *c_qkv = nullptr, *c_in = nullptr;
 };
 
 struct Mpnet {
@@ -63,6 +66,10 @@ struct Mpnet {
     h16 *h = nullptr, *h1 = nullptr, *tmp = nullptr, *ctx = nullptr, *qkv = nullptr, *ffn = nullptr;
     bool fp16 = false;
     bool fuse_ln = false;  // residual GEMMs carry the post-LN in their epilogue (cluster kernel)
+    // LayerNorm folded into the neighbouring GEMMs: producers write pre-LN rows + row partials,
+    // consumers carry gamma in their weights and finish the normalisation in the epilogue.
+    bool fold_ln = false;
+    float2 *stats_x = nullptr, *stats_y = nullptr;  // [H/128][max_tokens] (sum, sum of squares)
 
     template <typename T>
     int alloc(T** p, size_t count) {
@@ -89,6 +96,38 @@ struct Mpnet {
             for (size_t i = 0; i < count; ++i) tmpv[i] = __bfloat16_as_ushort(__float2bfloat16_rn(src[i]));
         }
         ARB_CHECK_CUDA(cudaMemcpy(dst, tmpv.data(), count * sizeof(h16), cudaMemcpyHostToDevice));
+        return ARB_OK;
+    }
+    // W'[n,k] = W[n,k] * gamma[k] rounded to 16 bit -> dst; colsum[n] = sum_k W'[n,k] (of the ROUNDED
+    // values, so that x W'^T - mean * colsum cancels exactly); bias_out[n] = bias[n] + sum_k W[n,k] beta[k]
+    int upload16_folded(h16* dst, float* colsum_dev, float* bias_dev, const float* w, const float* bias,
+                        const float* gamma, const float* beta, size_t N, size_t K) {
+        ARB_REQUIRE(w && bias && gamma && beta, "mpnet_create: missing weight array");
+        std::vector<h16> t16(N * K);
+        std::vector<float> cs(N), bo(N);
+        for (size_t n = 0; n < N; ++n) {
+            double c = 0.0, b = bias[n];
+            for (size_t k = 0; k < K; ++k) {
+                const float wf = w[n * K + k] * gamma[k];
+                float back;
+                if (fp16) {
+                    const __half hv = __float2half_rn(wf);
+                    t16[n * K + k] = __half_as_ushort(hv);
+                    back = __half2float(hv);
+                } else {
+                    const __nv_bfloat16 bv = __float2bfloat16_rn(wf);
+                    t16[n * K + k] = __bfloat16_as_ushort(bv);
+                    back = __bfloat162float(bv);
+                }
+                c += back;
+                b += static_cast<double>(w[n * K + k]) * beta[k];
+            }
+            cs[n] = static_cast<float>(c);
+            bo[n] = static_cast<float>(b);
+        }
+        ARB_CHECK_CUDA(cudaMemcpy(dst, t16.data(), N * K * sizeof(h16), cudaMemcpyHostToDevice));
+        ARB_CHECK_CUDA(cudaMemcpy(colsum_dev, cs.data(), N * 4, cudaMemcpyHostToDevice));
+        ARB_CHECK_CUDA(cudaMemcpy(bias_dev, bo.data(), N * 4, cudaMemcpyHostToDevice));
         return ARB_OK;
     }
     ~Mpnet() {
@@ -121,22 +160,41 @@ static int mpnet_build(Mpnet* m, const ArbMpnetWeights* w) {
         const ArbMpnetLayerWeights& lw = w->layers[l];
         LayerDev& d = m->layers[l];
         if (int rc = m->alloc(&d.w_qkv, 3 * H * H)) return rc;
-        if (int rc = m->upload16(d.w_qkv, lw.q_w, H * H)) return rc;
-        if (int rc = m->upload16(d.w_qkv + H * H, lw.k_w, H * H)) return rc;
-        if (int rc = m->upload16(d.w_qkv + 2 * H * H, lw.v_w, H * H)) return rc;
         if (int rc = m->alloc(&d.b_qkv, 3 * H)) return rc;
         ARB_REQUIRE(lw.q_b && lw.k_b && lw.v_b, "mpnet_create: missing q/k/v bias (layer %d)", l);
-        ARB_CHECK_CUDA(cudaMemcpy(d.b_qkv, lw.q_b, H * 4, cudaMemcpyHostToDevice));
-        ARB_CHECK_CUDA(cudaMemcpy(d.b_qkv + H, lw.k_b, H * 4, cudaMemcpyHostToDevice));
-        ARB_CHECK_CUDA(cudaMemcpy(d.b_qkv + 2 * H, lw.v_b, H * 4, cudaMemcpyHostToDevice));
+        if (m->fold_ln && l > 0) {
+            // the q/k/v projections of layer l read LN2 of layer l-1: carry its gamma/beta
+            const ArbMpnetLayerWeights& pw = w->layers[l - 1];
+            if (int rc = m->alloc(&d.c_qkv, 3 * H)) return rc;
+            const float* ws[3] = {lw.q_w, lw.k_w, lw.v_w};
+            const float* bs[3] = {lw.q_b, lw.k_b, lw.v_b};
+            for (int t = 0; t < 3; ++t)
+                if (int rc = m->upload16_folded(d.w_qkv + t * H * H, d.c_qkv + t * H, d.b_qkv + t * H, ws[t], bs[t],
+                                                pw.out_ln_g, pw.out_ln_b, H, H))
+                    return rc;
+        } else {
+            if (int rc = m->upload16(d.w_qkv, lw.q_w, H * H)) return rc;
+            if (int rc = m->upload16(d.w_qkv + H * H, lw.k_w, H * H)) return rc;
+            if (int rc = m->upload16(d.w_qkv + 2 * H * H, lw.v_w, H * H)) return rc;
+            ARB_CHECK_CUDA(cudaMemcpy(d.b_qkv, lw.q_b, H * 4, cudaMemcpyHostToDevice));
+            ARB_CHECK_CUDA(cudaMemcpy(d.b_qkv + H, lw.k_b, H * 4, cudaMemcpyHostToDevice));
+            ARB_CHECK_CUDA(cudaMemcpy(d.b_qkv + 2 * H, lw.v_b, H * 4, cudaMemcpyHostToDevice));
+        }
         if (int rc = m->alloc(&d.w_o, H * H)) return rc;
         if (int rc = m->upload16(d.w_o, lw.o_w, H * H)) return rc;
         if (int rc = m->upload_f32(&d.b_o, lw.o_b, H)) return rc;
         if (int rc = m->upload_f32(&d.ln1_g, lw.attn_ln_g, H)) return rc;
         if (int rc = m->upload_f32(&d.ln1_b, lw.attn_ln_b, H)) return rc;
         if (int rc = m->alloc(&d.w_in, I * H)) return rc;
-        if (int rc = m->upload16(d.w_in, lw.ffn_in_w, I * H)) return rc;
-        if (int rc = m->upload_f32(&d.b_in, lw.ffn_in_b, I)) return rc;
+        if (m->fold_ln) {  // the FFN up-projection reads LN1 of this layer
+            if (int rc = m->alloc(&d.c_in, I)) return rc;
+            if (int rc = m->alloc(&d.b_in, I)) return rc;
+            if (int rc = m->upload16_folded(d.w_in, d.c_in, d.b_in, lw.ffn_in_w, lw.ffn_in_b, lw.attn_ln_g, lw.attn_ln_b, I, H))
+                return rc;
+        } else {
+            if (int rc = m->upload16(d.w_in, lw.ffn_in_w, I * H)) return rc;
+            if (int rc = m->upload_f32(&d.b_in, lw.ffn_in_b, I)) return rc;
+        }
         if (int rc = m->alloc(&d.w_out, H * I)) return rc;
         if (int rc = m->upload16(d.w_out, lw.ffn_out_w, H * I)) return rc;
         if (int rc = m->upload_f32(&d.b_out, lw.ffn_out_b, H)) return rc;
@@ -150,6 +208,10 @@ static int mpnet_build(Mpnet* m, const ArbMpnetWeights* w) {
     if (int rc = m->alloc(&m->ctx, T * H)) return rc;
     if (int rc = m->alloc(&m->qkv, T * 3 * H)) return rc;
     if (int rc = m->alloc(&m->ffn, T * I)) return rc;
+    if (m->fold_ln) {
+        if (int rc = m->alloc(&m->stats_x, T * (H / 128))) return rc;
+        if (int rc = m->alloc(&m->stats_y, T * (H / 128))) return rc;
+    }
     return ARB_OK;
 }
 
@@ -163,6 +225,49 @@ static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B
                               c.vocab_size, c.max_position_embeddings, c.pad_token_id, c.position_mode,
                               c.layer_norm_eps, m->fp16, st)))
         return rc;
+    if (m->fold_ln) {
+        // No LayerNorm passes between the GEMMs: x (pre-LN, in `tmp`) and y (pre-LN, in `h1`) travel
+        // with their row partials; every consumer finishes the normalisation in its epilogue.
+        LnFoldArgs f;
+        f.parts_in = H / 128;
+        f.inv_width_in = 1.0f / static_cast<float>(H);
+        f.eps = c.layer_norm_eps;
+        for (int l = 0; l < c.num_layers; ++l) {
+            const LayerDev& d = m->layers[l];
+            LnFoldArgs fq = f, fo = f, fu = f, fd = f;
+            if (l == 0) {  // the embedding LayerNorm output is already normalised
+                if ((rc = launch_gemm16(m->h, H, d.w_qkv, H, m->qkv, 3 * H, d.b_qkv, nullptr, 0, T, 3 * H, H, EPI_BIAS, m->fp16, st))) return rc;
+            } else {
+                fq.colsum = d.c_qkv;
+                fq.stats_in = m->stats_x;
+                if ((rc = launch_gemm16_fold(m->tmp, H, d.w_qkv, H, m->qkv, 3 * H, d.b_qkv, nullptr, 0, T, 3 * H, H, EPI_LNIN_BIAS, fq, m->fp16, st))) return rc;
+            }
+            if ((rc = launch_attention(m->qkv, m->rel_bias, m->max_seq, mask, m->ctx, B, S, c.num_heads, H / c.num_heads, m->fp16, 0, st))) return rc;
+            // y = ctx Wo^T + bo + LN2_{l-1}(x)   (layer 0: + h), row partials of y
+            fo.stats_out = m->stats_y;
+            if (l == 0) {
+                if ((rc = launch_gemm16_fold(m->ctx, H, d.w_o, H, m->h1, H, d.b_o, m->h, H, T, H, H, EPI_BIAS_RES_STATS, fo, m->fp16, st))) return rc;
+            } else {
+                fo.gamma = m->layers[l - 1].ln2_g;
+                fo.beta = m->layers[l - 1].ln2_b;
+                fo.stats_in = m->stats_x;
+                if ((rc = launch_gemm16_fold(m->ctx, H, d.w_o, H, m->h1, H, d.b_o, m->tmp, H, T, H, H, EPI_BIAS_LNRES_STATS, fo, m->fp16, st))) return rc;
+            }
+            // ffn = gelu(LN1(y) W1^T + b1)
+            fu.colsum = d.c_in;
+            fu.stats_in = m->stats_y;
+            if ((rc = launch_gemm16_fold(m->h1, H, d.w_in, H, m->ffn, I, d.b_in, nullptr, 0, T, I, H, EPI_LNIN_BIAS_GELU, fu, m->fp16, st))) return rc;
+            // x = ffn W2^T + b2 + LN1(y), row partials of x
+            fd.gamma = d.ln1_g;
+            fd.beta = d.ln1_b;
+            fd.stats_in = m->stats_y;
+            fd.stats_out = m->stats_x;
+            if ((rc = launch_gemm16_fold(m->ffn, I, d.w_out, I, m->tmp, H, d.b_out, m->h1, H, T, H, I, EPI_BIAS_LNRES_STATS, fd, m->fp16, st))) return rc;
+        }
+        const LayerDev& last = m->layers[c.num_layers - 1];
+        if ((rc = launch_layernorm(m->tmp, last.ln2_g, last.ln2_b, m->h, T, H, c.layer_norm_eps, m->fp16, st))) return rc;
+        return launch_pool_normalize(m->h, mask, out, B, S, H, m->fp16, st);
+    }
     for (int l = 0; l < c.num_layers; ++l) {
         const LayerDev& d = m->layers[l];
         // q,k,v projections as one [T,H] x [3H,H]^T GEMM (modeling_mpnet.py:145-159)
@@ -243,6 +348,11 @@ int arb_mpnet_create(const ArbMpnetConfig* cfg, const ArbMpnetWeights* weights, 
     // accumulators exist to hide it. It stays available through arb_gemm16_residual_ln; the
     // encoder keeps the two-kernel path until the chain is shortened.
     m->fuse_ln = false;
+    // What the encoder does instead: fold the LayerNorms into the neighbouring GEMM epilogues
+    // (EPI_LNIN_* / EPI_*_STATS, kernels.h). ARB_FOLD_LN=0 keeps the GEMM + LayerNorm-pass path
+    // (the A/B baseline; both are parity-tested).
+    const char* fold_env = getenv("ARB_FOLD_LN");
+    m->fold_ln = !(fold_env && fold_env[0] == '0');
     m->device = device;
     m->max_tokens = max_tokens;
     m->max_seq = max_seq;
@@ -266,6 +376,7 @@ int64_t arb_mpnet_device_bytes(void* handle) { return handle ? static_cast<Mpnet
 int arb_mpnet_launches_per_encode(void* handle) {
     if (!handle) return 0;
     const Mpnet* m = static_cast<Mpnet*>(handle);
+    if (m->fold_ln) return 3 + 5 * m->cfg.num_layers;  // embed, 5 per layer, final LayerNorm, pool
     return 2 + (m->fuse_ln ? 5 : 7) * m->cfg.num_layers;
 }
 
@@ -308,6 +419,27 @@ int arb_topk_merge(const float* scores_dev, const int64_t* ids_dev, int32_t G, i
                    float* out_scores_dev, int64_t* out_ids_dev, void* stream) {
     return launch_topk_merge(scores_dev, ids_dev, G, Q, k, out_scores_dev, out_ids_dev,
                              static_cast<cudaStream_t>(stream));
+}
+
+static int dtype16(int32_t dtype, bool* fp16);
+
+int arb_gemm16_lnfold(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias,
+                      const void* R, int64_t ldr, const float* colsum, const float* gamma, const float* beta,
+                      const float* stats_in, int32_t parts_in, int32_t width_in, float* stats_out, float eps, int64_t M,
+                      int32_t N, int32_t K, int32_t epilogue, int32_t dtype, void* stream) {
+    bool fp16;
+    if (int rc = dtype16(dtype, &fp16)) return rc;
+    LnFoldArgs f;
+    f.colsum = colsum;
+    f.gamma = gamma;
+    f.beta = beta;
+    f.stats_in = reinterpret_cast<const float2*>(stats_in);
+    f.stats_out = reinterpret_cast<float2*>(stats_out);
+    f.parts_in = parts_in;
+    f.inv_width_in = width_in > 0 ? 1.0f / static_cast<float>(width_in) : 0.f;
+    f.eps = eps;
+    return launch_gemm16_fold(static_cast<const h16*>(A), lda, static_cast<const h16*>(B), ldb, static_cast<h16*>(C), ldc, bias,
+                              static_cast<const h16*>(R), ldr, M, N, K, epilogue, f, fp16, static_cast<cudaStream_t>(stream));
 }
 
 size_t arb_topk_exchange_bytes(int32_t G, size_t slot_bytes) { return G > 0 ? topk_exchange_bytes(G, slot_bytes) : 0; }

@@ -108,10 +108,15 @@ template <int EPI, bool kF16, typename OutT, bool k2Cta>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
-              const float* __restrict__ bias, int64_t M, int N, int K) {
+              const float* __restrict__ bias, int64_t M, int N, int K, const LnFoldArgs fold) {
     constexpr int BN = kGemmBN;
     constexpr int CW = 128 / static_cast<int>(sizeof(OutT));  // columns per staging chunk
     constexpr int CPG = (BN / 2) / CW;                        // chunks per group per tile
+    constexpr bool kLnIn = EPI == EPI_LNIN_BIAS || EPI == EPI_LNIN_BIAS_GELU;
+    constexpr bool kGelu = EPI == EPI_BIAS_GELU || EPI == EPI_LNIN_BIAS_GELU;
+    constexpr bool kRes = EPI == EPI_BIAS_RESIDUAL || EPI == EPI_BIAS_LNRES_STATS || EPI == EPI_BIAS_RES_STATS;
+    constexpr bool kLnRes = EPI == EPI_BIAS_LNRES_STATS;
+    constexpr bool kStats = EPI == EPI_BIAS_LNRES_STATS || EPI == EPI_BIAS_RES_STATS;
     using SM = typename std::conditional<k2Cta, Gemm2Smem, GemmSmem>::type;
     using Iter = typename std::conditional<k2Cta, Gemm2TileIter, GemmTileIter>::type;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -155,36 +160,76 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         const int lane_grp = warp & 3;   // TMEM lanes [32*lane_grp, +32) are the only ones this warp may read
         const int trow = lane_grp * 32 + lane;
         const bool leader = (ew & 3) == 0 && lane == 0;  // issues the group's TMA traffic
-        // kBufs staging tiles per group. With two, chunk c of a tile uses tile c & 1: a store is
-        // still draining from one while the next chunk is written into the other, and (residual
-        // epilogue) both residual chunks of the NEXT tile are fetched before its accumulator is
-        // even complete, so neither TMA latency sits on the epilogue's critical path.
+        // kBufs staging tiles per group. With two, consecutive live chunks alternate between them: a
+        // TMA store is still draining from one while the next chunk is written into the other, and
+        // (residual epilogues) the residual of chunk k+1 is requested right after the store of chunk
+        // k is issued, so it has a whole chunk of epilogue work to arrive (also across tiles).
         constexpr int kBufs = kGemmStageBufs<k2Cta>;
-        static_assert(kBufs == 1 || EPI != EPI_BIAS_RESIDUAL || CPG == 2, "residual prefetch assumes two chunks per tile");
         uint8_t* stage_base = sm.pre() + grp * kBufs * kStageTileBytes;
         const int sw = trow & 7;
         uint32_t res_phase = 0;  // bit b = parity of the next completion of this group's residual barrier b
+        int kc = 0;              // live chunks processed so far by this group
         if (leader) {
             tma_prefetch_desc(&tmap_c);
-            if (EPI == EPI_BIAS_RESIDUAL) tma_prefetch_desc(&tmap_r);
+            if (kRes) tma_prefetch_desc(&tmap_r);
+        }
+        // residual prefetch cursor (leader thread, kBufs == 2): walks the same (tile, chunk) sequence
+        // one live chunk ahead of the epilogue
+        Iter pf_it = it;
+        int pf_ra = 0, pf_rb = 0, pf_c = CPG, pf_k = 0;
+        bool pf_valid = true;
+        auto prefetch_next_residual = [&]() {
+            while (pf_valid) {
+                if (++pf_c >= CPG) {
+                    pf_valid = pf_it.next(pf_ra, pf_rb);
+                    pf_c = 0;
+                }
+                if (pf_valid && pf_rb + grp * (BN / 2) + pf_c * CW < N) break;
+            }
+            if (!pf_valid) return;
+            const int b = pf_k & 1;
+            mbar_arrive_expect_tx(sm.aux(grp * 2 + b), kStageTileBytes);
+            tma_load_2d(&tmap_r, sm.aux(grp * 2 + b), stage_base + b * kStageTileBytes,
+                        pf_rb + grp * (BN / 2) + pf_c * CW, pf_ra, kEvictFirst);
+            ++pf_k;
+        };
+        if (kRes && kBufs == 2 && leader) prefetch_next_residual();
+        // folded LayerNorm: the producer's row partials of the NEXT tile are requested a tile ahead
+        constexpr int kMaxParts = 8;
+        float2 pre[kMaxParts];
+        auto request_stats = [&](int64_t row) {
+#pragma unroll
+            for (int p = 0; p < kMaxParts; ++p)
+                pre[p] = (p < fold.parts_in && row < M) ? __ldg(fold.stats_in + static_cast<int64_t>(p) * M + row)
+                                                        : make_float2(0.f, 0.f);
+        };
+        if constexpr (kLnIn || kLnRes) {
+            Iter pk = it;
+            int ra2, rb2;
+            if (pk.next(ra2, rb2)) request_stats(static_cast<int64_t>(ra2) + trow);
         }
         int acc = 0;
         uint32_t acc_phase = 0;
         int row_a, row_b;
         while (it.next(row_a, row_b)) {
-            if (EPI == EPI_BIAS_RESIDUAL && kBufs == 2 && leader) {
+            const int64_t grow = static_cast<int64_t>(row_a) + trow;
+            float rstd = 1.f, nmr = 0.f;  // nmr = -mean * rstd
+            if constexpr (kLnIn || kLnRes) {
+                float su = 0.f, sq = 0.f;
 #pragma unroll
-                for (int c = 0; c < CPG; ++c) {
-                    const int col0 = row_b + grp * (BN / 2) + c * CW;
-                    if (col0 < N) {
-                        // the store that last used this tile (same chunk, previous tile) has been read
-                        if (c == 0) tma_store_wait_read<1>();
-                        else tma_store_wait_read<0>();
-                        mbar_arrive_expect_tx(sm.aux(grp * 2 + c), kStageTileBytes);
-                        tma_load_2d(&tmap_r, sm.aux(grp * 2 + c), stage_base + c * kStageTileBytes, col0, row_a, kEvictFirst);
-                    }
+                for (int p = 0; p < kMaxParts; ++p) {
+                    su += pre[p].x;
+                    sq += pre[p].y;
                 }
+                const float mean = su * fold.inv_width_in;
+                rstd = rsqrtf(fmaxf(fmaf(-mean, mean, sq * fold.inv_width_in), 0.f) + fold.eps);
+                nmr = -mean * rstd;
+                Iter pk = it;  // `it` already points past this tile
+                int ra2, rb2;
+                if (pk.next(ra2, rb2)) request_stats(static_cast<int64_t>(ra2) + trow);
             }
+            float osum = 0.f, osq = 0.f;  // statistics of the rows this tile produces (kStats)
+            bool any_live = false;
             mbar_wait(sm.tmem_full(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
@@ -193,11 +238,11 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             for (int c = 0; c < CPG; ++c) {
                 const int col0 = row_b + grp * (BN / 2) + c * CW;
                 const bool live = col0 < N;  // group-uniform
-                const int buf = c & (kBufs - 1);
+                const int buf = kc & (kBufs - 1);
                 uint8_t* stage_tile = stage_base + buf * kStageTileBytes;
                 uint8_t* my_row = stage_tile + trow * 128;
                 uint64_t* res_bar = sm.aux(grp * 2 + buf);
-                if (EPI == EPI_BIAS_RESIDUAL && kBufs == 1 && live && leader) {
+                if (kRes && kBufs == 1 && live && leader) {
                     tma_store_wait_read<0>();  // the previous store has drained the staging tile
                     mbar_arrive_expect_tx(res_bar, kStageTileBytes);
                     tma_load_2d(&tmap_r, res_bar, stage_tile, col0, row_a, kEvictFirst);
@@ -217,10 +262,24 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
                     }
                 }
                 if (!live) continue;
+                any_live = true;
+                ++kc;
                 float v[CW];
 #pragma unroll
                 for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
-                if (bias != nullptr) {
+                if constexpr (kLnIn) {
+                    // LN(x) W^T + b = rstd (x W'^T) - mean rstd c + b'   (columns are whole 64-wide chunks here)
+                    const float4* bp = reinterpret_cast<const float4*>(bias + col0);
+                    const float4* cp = reinterpret_cast<const float4*>(fold.colsum + col0);
+#pragma unroll
+                    for (int j = 0; j < CW / 4; ++j) {
+                        const float4 b4 = __ldg(bp + j), c4 = __ldg(cp + j);
+                        v[4 * j + 0] = fmaf(rstd, v[4 * j + 0], fmaf(nmr, c4.x, b4.x));
+                        v[4 * j + 1] = fmaf(rstd, v[4 * j + 1], fmaf(nmr, c4.y, b4.y));
+                        v[4 * j + 2] = fmaf(rstd, v[4 * j + 2], fmaf(nmr, c4.z, b4.z));
+                        v[4 * j + 3] = fmaf(rstd, v[4 * j + 3], fmaf(nmr, c4.w, b4.w));
+                    }
+                } else if (bias != nullptr) {
                     // columns beyond N read zero bias via the clamp; they are clipped by the store
                     const float4* bp = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
@@ -234,20 +293,34 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
                         }
                     }
                 }
-                if (EPI == EPI_BIAS_GELU) {
+                if (kGelu) {
 #pragma unroll
                     for (int j = 0; j < CW; ++j) v[j] = kF16 ? gelu_erf(v[j]) : gelu_tanh_fit(v[j]);
                 }
-                if (EPI == EPI_BIAS_RESIDUAL) {
+                if (kRes) {
                     mbar_wait(res_bar, (res_phase >> buf) & 1u);
                     res_phase ^= 1u << buf;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const uint4 u = *reinterpret_cast<const uint4*>(my_row + ((j ^ sw) << 4));
                         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                        float gm[8], bt[8];
+                        if constexpr (kLnRes) {  // gamma / beta of the 8 columns of this 16-byte piece
+                            const float4* gp = reinterpret_cast<const float4*>(fold.gamma + col0 + 8 * j);
+                            const float4* bp = reinterpret_cast<const float4*>(fold.beta + col0 + 8 * j);
+                            const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), b0 = __ldg(bp), b1 = __ldg(bp + 1);
+                            gm[0] = g0.x; gm[1] = g0.y; gm[2] = g0.z; gm[3] = g0.w;
+                            gm[4] = g1.x; gm[5] = g1.y; gm[6] = g1.z; gm[7] = g1.w;
+                            bt[0] = b0.x; bt[1] = b0.y; bt[2] = b0.z; bt[3] = b0.w;
+                            bt[4] = b1.x; bt[5] = b1.y; bt[6] = b1.z; bt[7] = b1.w;
+                        }
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float2 f = unpack16x2<kF16>(w[q]);
+                            float2 f = unpack16x2<kF16>(w[q]);
+                            if constexpr (kLnRes) {  // the residual is LN(R) = rstd (R gamma) + (beta - mean rstd gamma)
+                                f.x = fmaf(rstd, f.x * gm[2 * q], fmaf(nmr, gm[2 * q], bt[2 * q]));
+                                f.y = fmaf(rstd, f.y * gm[2 * q + 1], fmaf(nmr, gm[2 * q + 1], bt[2 * q + 1]));
+                            }
                             v[8 * j + 2 * q] += f.x;
                             v[8 * j + 2 * q + 1] += f.y;
                         }
@@ -266,6 +339,16 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
                         u.z = pack16x2<kF16>(v[8 * j + 4], v[8 * j + 5]);
                         u.w = pack16x2<kF16>(v[8 * j + 6], v[8 * j + 7]);
                         *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = u;
+                        if constexpr (kStats) {
+                            // row statistics from the fp32 values: the 16-bit rounding the consumer sees
+                            // is zero-mean noise of 2^-9 relative size, far below the LayerNorm's own eps scale
+#pragma unroll
+                            for (int q = 0; q < 8; q += 2) {
+                                osum += v[8 * j + q] + v[8 * j + q + 1];
+                                osq = fmaf(v[8 * j + q], v[8 * j + q], osq);
+                                osq = fmaf(v[8 * j + q + 1], v[8 * j + q + 1], osq);
+                            }
+                        }
                     }
                 } else {
 #pragma unroll
@@ -278,7 +361,17 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
                 if (leader) {
                     tma_store_2d(&tmap_c, stage_tile, col0, row_a);
                     tma_store_commit();
+                    if (kRes && kBufs == 2) {
+                        // every store but the one just issued has been read: the other tile is free
+                        tma_store_wait_read<1>();
+                        prefetch_next_residual();
+                    }
                 }
+            }
+            if constexpr (kStats) {
+                // this thread covered columns [row_b + 128 grp, +128) of its row: one partial
+                if (any_live && grow < M)
+                    fold.stats_out[static_cast<int64_t>((row_b >> 7) + grp) * M + grow] = make_float2(osum, osq);
             }
             if (++acc == 2) {
                 acc = 0;
@@ -294,16 +387,17 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 template <int EPI, bool kF16, typename OutT>
 static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb, OutT* C,
                             int64_t ldc, const float* bias, const h16* R, int64_t ldr, int64_t M,
-                            int N, int K, cudaStream_t stream) {
+                            int N, int K, cudaStream_t stream, const LnFoldArgs& fold = LnFoldArgs()) {
+    constexpr bool kRes = EPI == EPI_BIAS_RESIDUAL || EPI == EPI_BIAS_LNRES_STATS || EPI == EPI_BIAS_RES_STATS;
     CUtensorMap ta, tb, tc, tr;
     // the TMA element type only matters for OOB fill; both 16-bit formats move as raw 2-byte words
     bool ok = make_tmap_bf16_k64(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), kBM) &&
               make_tmap_bf16_k64(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), kGemmBN) &&
               make_tmap_rows128(&tc, C, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldc), sizeof(OutT));
-    if (ok) ok = make_tmap_rows128(&tr, EPI == EPI_BIAS_RESIDUAL ? static_cast<const void*>(R) : static_cast<const void*>(C),
+    if (ok) ok = make_tmap_rows128(&tr, kRes ? static_cast<const void*>(R) : static_cast<const void*>(C),
                                    static_cast<uint64_t>(M), static_cast<uint64_t>(N),
-                                   static_cast<uint64_t>(EPI == EPI_BIAS_RESIDUAL ? ldr : ldc),
-                                   EPI == EPI_BIAS_RESIDUAL ? 2 : static_cast<int>(sizeof(OutT)));
+                                   static_cast<uint64_t>(kRes ? ldr : ldc),
+                                   kRes ? 2 : static_cast<int>(sizeof(OutT)));
     if (!ok) {
         set_error("cuTensorMapEncodeTiled failed (A %p lda %lld, B %p ldb %lld, C %p ldc %lld)", (const void*)A,
                   (long long)lda, (const void*)B, (long long)ldb, (const void*)C, (long long)ldc);
@@ -335,7 +429,7 @@ static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        ARB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tr, bias, M, N, K));
+        ARB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tr, bias, M, N, K, fold));
         return ARB_OK;
     }
     auto kern = gemm16_kernel<EPI, kF16, OutT, false>;
@@ -344,7 +438,7 @@ static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb
     ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + kGemmBN - 1) / kGemmBN);
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, tc, tr, bias, M, N, K);
+    kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, tc, tr, bias, M, N, K, fold);
     ARB_CHECK_CUDA(cudaGetLastError());
     return ARB_OK;
 }
@@ -629,6 +723,50 @@ int launch_gemm16(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, 
                 "gemm: bias must be 16-byte aligned");
     return fp16 ? dispatch_gemm16<true>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, stream)
                 : dispatch_gemm16<false>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, stream);
+}
+
+template <bool kF16>
+static int dispatch_gemm16_fold(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
+                                const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
+                                int epilogue, const LnFoldArgs& f, cudaStream_t stream) {
+    switch (epilogue) {
+        case EPI_LNIN_BIAS:
+            return launch_gemm_impl<EPI_LNIN_BIAS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, stream, f);
+        case EPI_LNIN_BIAS_GELU:
+            return launch_gemm_impl<EPI_LNIN_BIAS_GELU, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, stream, f);
+        case EPI_BIAS_LNRES_STATS:
+            return launch_gemm_impl<EPI_BIAS_LNRES_STATS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, stream, f);
+        default:
+            return launch_gemm_impl<EPI_BIAS_RES_STATS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, stream, f);
+    }
+}
+
+int launch_gemm16_fold(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
+                       const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
+                       int epilogue, const LnFoldArgs& f, bool fp16, cudaStream_t stream) {
+    int rc = check_gemm_args(A, lda, B, ldb, C, ldc, M, N, K, 2);
+    if (rc) return rc;
+    ARB_REQUIRE(epilogue >= EPI_LNIN_BIAS && epilogue <= EPI_BIAS_RES_STATS, "gemm_fold: unknown epilogue %d", epilogue);
+    ARB_REQUIRE(bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm_fold: bias missing or misaligned");
+    const bool ln_in = epilogue == EPI_LNIN_BIAS || epilogue == EPI_LNIN_BIAS_GELU;
+    const bool stats = epilogue == EPI_BIAS_LNRES_STATS || epilogue == EPI_BIAS_RES_STATS;
+    if (ln_in) {
+        ARB_REQUIRE(N % 64 == 0, "gemm_fold: N=%d must be a multiple of 64", N);
+        ARB_REQUIRE(f.colsum && (reinterpret_cast<uintptr_t>(f.colsum) & 15) == 0, "gemm_fold: colsum missing or misaligned");
+    }
+    if (stats) {
+        ARB_REQUIRE(N % 128 == 0, "gemm_fold: N=%d must be a multiple of 128 for row statistics", N);
+        ARB_REQUIRE(f.stats_out != nullptr, "gemm_fold: stats_out missing");
+        ARB_REQUIRE(R != nullptr && ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0,
+                    "gemm_fold: residual operand missing or misaligned");
+    }
+    if (ln_in || epilogue == EPI_BIAS_LNRES_STATS)
+        ARB_REQUIRE(f.stats_in != nullptr && f.parts_in > 0 && f.inv_width_in > 0.f, "gemm_fold: input row statistics missing");
+    if (epilogue == EPI_BIAS_LNRES_STATS)
+        ARB_REQUIRE(f.gamma && f.beta && (reinterpret_cast<uintptr_t>(f.gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(f.beta) & 15) == 0,
+                    "gemm_fold: gamma / beta missing or misaligned");
+    return fp16 ? dispatch_gemm16_fold<true>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, f, stream)
+                : dispatch_gemm16_fold<false>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, f, stream);
 }
 
 int launch_gemm16_ln(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,

@@ -13,12 +13,37 @@ enum GemmEpilogue : int {
     EPI_BIAS = 0,           // C = A.B^T + bias
     EPI_BIAS_GELU = 1,      // C = gelu_erf(A.B^T + bias)
     EPI_BIAS_RESIDUAL = 2,  // C = A.B^T + bias + R
+    // LayerNorm folded into the neighbouring GEMMs (no separate LayerNorm pass):
+    // the producer writes the PRE-LayerNorm rows x plus per-row (sum, sum of squares) partials; a
+    // consumer GEMM whose weights carry gamma (W' = W diag(gamma), colsum c = W' 1, bias b' = b + W beta)
+    // recovers LN(x) W^T + b = rstd (x W'^T - mu c) + b' in its epilogue.
+    EPI_LNIN_BIAS = 3,          // C = rstd (A.B'^T - mu c) + b'                (A rows are pre-LN)
+    EPI_LNIN_BIAS_GELU = 4,     // C = gelu(rstd (A.B'^T - mu c) + b')
+    EPI_BIAS_LNRES_STATS = 5,   // C = A.B^T + bias + LN(R); row partials of C -> stats_out
+    EPI_BIAS_RES_STATS = 6,     // C = A.B^T + bias + R;     row partials of C -> stats_out
+};
+
+// Extra operands of the folded-LayerNorm epilogues. Row statistics travel as partial sums:
+// part p of row r at stats[p * M + r] = (sum, sum of squares) over 128 columns of that row.
+struct LnFoldArgs {
+    const float* colsum = nullptr;     // c[N]                      (EPI_LNIN_*)
+    const float* gamma = nullptr;      // LayerNorm weight of R     (EPI_BIAS_LNRES_STATS)
+    const float* beta = nullptr;       // LayerNorm bias of R       (EPI_BIAS_LNRES_STATS)
+    const float2* stats_in = nullptr;  // partials of the rows being normalised (A rows / R rows)
+    float2* stats_out = nullptr;       // partials of the output rows, N / 128 parts (EPI_*_STATS)
+    int parts_in = 0;
+    float inv_width_in = 0.f;          // 1 / (columns the input partials cover)
+    float eps = 0.f;
 };
 
 // C[M,N] = epi(A[M,K] . B[N,K]^T); A, B, C, R 16-bit row-major; bias fp32 [N] (may be null).
 int launch_gemm16(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
                   const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
                   int epilogue, bool fp16, cudaStream_t stream);
+// The folded-LayerNorm epilogues (3..6); N % 128 == 0 for the *_STATS ones.
+int launch_gemm16_fold(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
+                       const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
+                       int epilogue, const LnFoldArgs& fold, bool fp16, cudaStream_t stream);
 // C = LayerNorm(A.B^T + bias + R) * gamma + beta in one kernel (cluster of N/256 CTAs per row block,
 // row statistics exchanged through distributed shared memory). N % 256 == 0, N <= 2048.
 bool gemm16_ln_supported(int N);

@@ -157,6 +157,18 @@ int arb_topk_search_launches(int32_t dtype);
  * callers that want to compose the encoder themselves. All pointers are device pointers;
  * `dtype` is the 16-bit activation format (ARB_DTYPE_BF16 or ARB_DTYPE_F16).
  * ------------------------------------------------------------------------------------------ */
+/* GEMM with a LayerNorm folded into its epilogue (how the encoder avoids separate LayerNorm passes).
+ * epilogue 3: C = rstd (A.B'^T - mean colsum) + bias          A rows are PRE-LayerNorm; B' = B diag(gamma),
+ *          4: same, then GELU                                   colsum[n] = sum_k B'[n,k], bias = b + B beta
+ *          5: C = A.B^T + bias + LayerNorm(R) (gamma, beta), and row partials of C -> stats_out
+ *          6: C = A.B^T + bias + R,                          and row partials of C -> stats_out
+ * Row statistics are partial sums: stats[p * M + r] = (sum, sum of squares) of 128 columns of row r as
+ * float2; stats_in has parts_in parts covering width_in columns (of A's rows for 3/4, of R's for 5);
+ * stats_out receives N / 128 parts (N % 128 == 0). */
+int arb_gemm16_lnfold(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias,
+                      const void* R, int64_t ldr, const float* colsum, const float* gamma, const float* beta,
+                      const float* stats_in, int32_t parts_in, int32_t width_in, float* stats_out, float eps, int64_t M,
+                      int32_t N, int32_t K, int32_t epilogue, int32_t dtype, void* stream);
 /* Tile schedule of the arb_gemm16* kernels (process-wide; for tests and benchmarks): 0 = auto,
  * 1 = one CTA per 128x256 tile (tcgen05 cta_group::1), 2 = CTA pairs sharing a 256x256 tile
  * (cta_group::2, thread-block clusters of two). Auto picks pairs for large M. */

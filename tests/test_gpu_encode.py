@@ -110,6 +110,26 @@ def test_oracle_parity_large_batch_pair_gemm(cuda, full_model):
     enc.close()
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+def test_layernorm_fold_matches_unfolded_path(cuda, full_model, dtype, monkeypatch):
+    """The encoder folds every inner LayerNorm into the neighbouring GEMM epilogues (default);
+    ARB_FOLD_LN=0 keeps GEMM + LayerNorm passes. Both meet the oracle bar and agree with each other
+    to well inside it (they differ only in where the 16-bit roundings fall)."""
+    arch, sd, model = full_model
+    ids, mask = eo.synthetic_tokens(9, 77, seed=19)
+    ref = eo.oracle_encode(model, ids, mask)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("ARB_FOLD_LN", flag)
+        enc = _encoder(arch, sd, dtype, max_batch=16, max_seq=128)
+        assert enc.launches_per_encode == (3 + 5 * 12 if flag == "1" else 2 + 7 * 12)
+        outs.append(enc.encode((ids, mask), batch_size=16, normalize_embeddings=True))
+        _assert_parity(outs[-1], ref, mask, dtype)
+        enc.close()
+    # two independent 16-bit computations: same order of agreement as each has with the oracle
+    assert _cos(outs[0], outs[1]).min() >= (COS_TOL_BF16_SHORT if dtype == "bf16" else 0.99999)
+
+
 def test_eps_is_a_parameter(cuda):
     """layer_norm_eps 1e-12 (installed MPNetConfig default) as well as 1e-5 (published config)."""
     arch = MPNetArch(vocab_size=1000, num_layers=2, layer_norm_eps=1e-12)

@@ -102,6 +102,67 @@ def test_gemm_pair_schedule_epilogues(lib, cuda, pair_schedule, dt, epi, shape):
     assert _rel_err(C, ref) < tol
 
 
+def _row_partials(x16, parts):
+    """(sum, sum of squares) over `parts` column blocks of 128, layout [parts][M] float2."""
+    xf = x16.float()
+    M = xf.shape[0]
+    blocks = xf.view(M, parts, 128)
+    return torch.stack([blocks.sum(2), (blocks * blocks).sum(2)], dim=2).permute(1, 0, 2).contiguous()  # [parts, M, 2]
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+@pytest.mark.parametrize("shape", [(777, 768, 768), (3000, 384, 384)])
+def test_gemm_layernorm_fold(lib, cuda, dt, shape, mode):
+    """The LayerNorm-folding epilogues the encoder uses instead of LayerNorm passes
+    (modeling_mpnet.py:210 / :242 post-LN): a producer writes pre-LN rows + row partials
+    (epilogue 6, then 5 with the normalised residual), consumers apply LN through gamma-scaled
+    weights, column sums and the partials (epilogues 3, 4). Reference: torch layer_norm + linear."""
+    import torch.nn.functional as F
+
+    tdt, code, tol = DT[dt]
+    M, H, K = shape
+    torch.manual_seed(5)
+    parts = H // 128
+    eps = 1e-5
+    x = (torch.randn(M, H, device=cuda) * 1.7 + 0.4).to(tdt)  # pre-LN rows with a non-zero mean
+    g = torch.randn(H, device=cuda) * 0.2 + 1.0
+    b = torch.randn(H, device=cuda) * 0.1
+    st_x = _row_partials(x, parts)
+    ln_x = F.layer_norm(x.float(), (H,), g, b, eps)
+    _lib.check(lib.arb_set_gemm_mode(mode))
+    try:
+        # consumer: C = [gelu](LN(x) W^T + bias) through folded weights
+        N = 3 * H
+        W = torch.randn(N, H, device=cuda) * 0.05
+        bias = torch.randn(N, device=cuda)
+        Wf = (W * g[None, :]).to(tdt)
+        colsum = Wf.float().sum(1).contiguous()
+        bias_f = (bias + W @ b).contiguous()
+        ref = ln_x @ W.T + bias
+        for epi, r in ((3, ref), (4, F.gelu(ref))):
+            C = torch.zeros(M, N, device=cuda, dtype=tdt)
+            _lib.check(lib.arb_gemm16_lnfold(x.data_ptr(), H, Wf.data_ptr(), H, C.data_ptr(), N, bias_f.data_ptr(), 0, 0,
+                                             colsum.data_ptr(), 0, 0, st_x.data_ptr(), parts, H, 0, eps, M, N, H, epi, code, _stream()))
+            assert _rel_err(C, r) < 2 * tol, (epi, _rel_err(C, r))
+        # producer: C = A Wo^T + bo + LN(x) (5) / + x (6), plus the row partials of the rounded C
+        A = (torch.randn(M, K, device=cuda) * 0.3).to(tdt)
+        Wo = (torch.randn(H, K, device=cuda) * 0.05).to(tdt)
+        bo = torch.randn(H, device=cuda)
+        base = A.float() @ Wo.float().T + bo
+        for epi, r in ((5, base + ln_x), (6, base + x.float())):
+            C = torch.zeros(M, H, device=cuda, dtype=tdt)
+            st_out = torch.full((parts, M, 2), float("nan"), device=cuda)
+            _lib.check(lib.arb_gemm16_lnfold(A.data_ptr(), K, Wo.data_ptr(), K, C.data_ptr(), H, bo.data_ptr(), x.data_ptr(), H,
+                                             0, g.data_ptr(), b.data_ptr(), st_x.data_ptr(), parts, H, st_out.data_ptr(), eps,
+                                             M, H, K, epi, code, _stream()))
+            assert _rel_err(C, r) < tol, (epi, _rel_err(C, r))
+            want = _row_partials(r, parts)  # statistics of the fp32 values before the 16-bit rounding
+            assert torch.allclose(st_out, want, rtol=2e-3, atol=0.05), (epi, (st_out - want).abs().max())
+    finally:
+        _lib.check(lib.arb_set_gemm_mode(0))
+
+
 def test_gemm_schedules_agree_bitwise(lib, cuda):
     """Both schedules accumulate each output element over K in the same order, so they must agree
     bit for bit — the encoder's result does not depend on which one `auto` picks."""

@@ -385,6 +385,34 @@ def stage_gemm2():
     return ok
 
 
+def stage_foldperf():
+    """The encoder's four GEMM shapes with plain epilogues (+ LayerNorm pass) and with the folded-LN epilogues."""
+    M, H, I = 1024 * 384, 768, 3072
+    parts = H // 128
+    x = torch.randn(M, H, device=DEV).to(torch.bfloat16)
+    st = torch.rand(parts, M, 2, device=DEV) * 100 + 200
+    g = torch.ones(H, device=DEV)
+    b = torch.zeros(H, device=DEV)
+    for (N, K, plain, fold) in [(2304, 768, 0, 3), (768, 768, 2, 5), (3072, 768, 1, 4), (768, 3072, 2, 5)]:
+        A = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+        B = (torch.randn(N, K, device=DEV) * 0.05).to(torch.bfloat16)
+        C = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+        bias = torch.randn(N, device=DEV)
+        cs = torch.randn(N, device=DEV)
+        so = torch.empty(N // 128, M, 2, device=DEV)
+        R = x if plain == 2 else None
+        t0 = _time(lambda: _lib.check(lib().arb_gemm16(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, bias.data_ptr(),
+                                                       R.data_ptr() if R is not None else 0, N, M, N, K, plain, _lib.ARB_DTYPE_BF16, stream())),
+                   iters=10, warm=3)
+        t1 = _time(lambda: _lib.check(lib().arb_gemm16_lnfold(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, bias.data_ptr(),
+                                                              x.data_ptr() if fold == 5 else 0, H, cs.data_ptr(), g.data_ptr(), b.data_ptr(),
+                                                              st.data_ptr(), parts, H, so.data_ptr() if fold == 5 else 0, 1e-5, M, N, K, fold,
+                                                              _lib.ARB_DTYPE_BF16, stream())), iters=10, warm=3)
+        print(f"gemm N{N} K{K}: plain epi{plain} {t0:.3f} ms | folded epi{fold} {t1:.3f} ms", flush=True)
+        del A, B, C
+    return True
+
+
 def stage_searchperf():
     """Search only: small-shard / small-Q (HBM-bound, the 8-GPU regime) and large-k cases, plus a
     per-kernel breakdown of one call from the CUPTI activity records (torch.profiler)."""
@@ -416,7 +444,7 @@ def stage_searchperf():
     return True
 
 
-STAGES = {"gemm2": stage_gemm2, "searchperf": stage_searchperf, "gemm": stage_gemm, "gemmln": stage_gemmln, "rowops": stage_rowops, "attention": stage_attention, "search": stage_search,
+STAGES = {"foldperf": stage_foldperf, "gemm2": stage_gemm2, "searchperf": stage_searchperf, "gemm": stage_gemm, "gemmln": stage_gemmln, "rowops": stage_rowops, "attention": stage_attention, "search": stage_search,
           "encode": stage_encode, "perf": stage_perf}
 
 if __name__ == "__main__":
