@@ -24,6 +24,10 @@ C = torch.empty(M, 3072, device=dev, dtype=torch.bfloat16)
 R = torch.randn(M, 768, device=dev).to(torch.bfloat16)
 Ws = {(N, K): (torch.randn(N, K, device=dev) * 0.04).to(torch.bfloat16) for (N, K) in [(2304, 768), (768, 768), (3072, 768), (768, 3072)]}
 bias = torch.randn(3072, device=dev)
+colsum = torch.randn(3072, device=dev)
+ln_g, ln_b = torch.ones(768, device=dev), torch.zeros(768, device=dev)
+stats_in = torch.rand(6, M, 2, device=dev) * 50 + 100
+stats_out = torch.empty(6, M, 2, device=dev)
 qkv = torch.randn(M, 3 * H, device=dev).to(torch.bfloat16)
 relb = torch.randn(12, 1023, device=dev)
 mask = torch.ones(B, S, device=dev, dtype=torch.int32)
@@ -37,10 +41,12 @@ os_ = torch.empty(4096, 10, device=dev)
 oi = torch.empty(4096, 10, device=dev, dtype=torch.int64)
 
 for rep in range(2):
-    for (N, K, epi) in [(2304, 768, 0), (768, 768, 2), (3072, 768, 1), (768, 3072, 2)]:
+    for (N, K, epi) in [(2304, 768, 3), (768, 768, 5), (3072, 768, 4), (768, 3072, 5)]:  # the encode path's folded-LN epilogues
         A = A768 if K == 768 else A3072
-        _lib.check(lib.arb_gemm16(A.data_ptr(), K, Ws[(N, K)].data_ptr(), K, C.data_ptr(), N, bias.data_ptr(),
-                                  R.data_ptr() if epi == 2 else 0, 768, M, N, K, epi, _lib.ARB_DTYPE_BF16, st()))
+        _lib.check(lib.arb_gemm16_lnfold(A.data_ptr(), K, Ws[(N, K)].data_ptr(), K, C.data_ptr(), N, bias.data_ptr(),
+                                         R.data_ptr() if epi == 5 else 0, 768, colsum.data_ptr(), ln_g.data_ptr(), ln_b.data_ptr(),
+                                         stats_in.data_ptr(), 6, 768, stats_out.data_ptr() if epi == 5 else 0, 1e-5, M, N, K, epi,
+                                         _lib.ARB_DTYPE_BF16, st()))
     _lib.check(lib.arb_attention16(qkv.data_ptr(), relb.data_ptr(), 512, mask.data_ptr(), ctx.data_ptr(), B, S, 12, 64,
                                    _lib.ARB_DTYPE_BF16, 0, st()))
     for Q in (4096, 64):
