@@ -256,7 +256,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
                     tc_fence_before();
                     if constexpr (k2Cta) {  // one arrival per warp on the leader CTA's barrier
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(sm.tmem_empty(acc)), 0));
+                        if (lane == 0) mbar_arrive_remote_cta(map_to_cta(smem_u32(sm.tmem_empty(acc)), 0));
                     } else {
                         mbar_arrive(sm.tmem_empty(acc));
                     }

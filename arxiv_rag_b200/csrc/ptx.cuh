@@ -106,6 +106,12 @@ __device__ __forceinline__ float2 ld_dsmem_f32x2(uint32_t cluster_addr) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same, without widening the release to cluster scope: for arrivals that only order this thread's
+// own tcgen05 / register work (e.g. "my warp has drained its TMEM accumulator rows"), where the
+// cluster-scope release's MEMBAR + ERRBAR (~1 us per arrive) buys nothing.
+__device__ __forceinline__ void mbar_arrive_remote_cta(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // wait on a local mbarrier whose arrivals come from other CTAs (acquire at cluster scope)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0;

@@ -230,7 +230,10 @@ __device__ __forceinline__ void pipe2_mma(const SM& sm, uint32_t tmem_base, Tile
     uint32_t acc_phase = 0;
     int row_a, row_b;
     while (it.next(row_a, row_b)) {
-        mbar_wait_cluster(sm.tmem_empty(acc), acc_phase ^ 1);
+        // CTA-scope acquire on purpose: the arrivals only order tcgen05.ld completions (made visible
+        // by tcgen05.fence), and a cluster-scope acquire would make ptxas invalidate the whole L1
+        // (CCTL.IVALL) once per tile — the cache the epilogue warps keep bias / gamma / beta in.
+        mbar_wait(sm.tmem_empty(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * SM::kBN;
         for (int kb = 0; kb < kblocks; ++kb) {
