@@ -138,7 +138,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     }
 
     uint32_t tmem_base;
-    if constexpr (k2Cta) tmem_base = pipe2_setup(sm, warp, &tmap_a, &tmap_b);
+    if constexpr (k2Cta) tmem_base = pipe2_setup(sm, warp, &tmap_a, &tmap_b, 2 * kEpiWarps);
     else tmem_base = pipe_setup(sm, warp, &tmap_a, &tmap_b, kEpiThreads);
 
     if (warp == 0) {

@@ -25,18 +25,25 @@ constexpr int kMaxK = 128;    // k <= 16: lists in registers; else 128 rows x k 
 // smem ring depth: 4 x 48 KB stages for k <= 16, 3 while list + a >= 16-candidate buffer fit, else 2
 
 struct SearchPlan {
-    int nq;        // 128-query tiles
+    bool pair;     // CTA-pair schedule (two query tiles per work item)
+    int nq;        // 128-query tiles, or pairs of them
     int nchunks;   // corpus chunks of kSBN rows
     int nsplit;    // corpus splits
     int cps;       // chunks per split (last split may be short)
-    int grid;
+    int grid;      // CTAs
 };
+
+// 0 = auto (pairs as soon as there is more than one query tile), 1 = single CTA, 2 = pairs
+static int g_search_mode = 0;
+void set_search_mode(int mode) { g_search_mode = mode; }
 
 static SearchPlan make_plan(int64_t Q, int64_t N, int k) {
     SearchPlan p;
-    p.nq = static_cast<int>((Q + kBM - 1) / kBM);
+    const int tiles = static_cast<int>((Q + kBM - 1) / kBM);
+    p.pair = g_search_mode == 2 || (g_search_mode == 0 && tiles > 1);
+    p.nq = p.pair ? (tiles + 1) / 2 : tiles;
     p.nchunks = static_cast<int>((N + kSBN - 1) / kSBN);
-    const int G = num_sms();
+    const int G = p.pair ? num_sms() / 2 : num_sms();  // schedulable units: CTAs or CTA pairs
     // Every item (split x query tile) starts with empty lists and pays a warm-up while its k-th
     // best is still low: ~k (1 + ln(rows/k)) survivors per query row have to be merged, which for
     // the shared-memory lists (k > 16) costs about 1.4 k chunk-times of epilogue work per item,
@@ -62,22 +69,24 @@ static SearchPlan make_plan(int64_t Q, int64_t N, int k) {
     p.nsplit = best;
     p.cps = (p.nchunks + best - 1) / best;
     const int64_t items = static_cast<int64_t>(p.nq) * p.nsplit;
-    p.grid = static_cast<int>(items < G ? items : G);
+    p.grid = static_cast<int>(items < G ? items : G) * (p.pair ? 2 : 1);
     return p;
 }
 
 // Yields the (query-tile row, corpus chunk row) sequence of this CTA's items.
+// nq = query tiles (single CTA) or query-tile PAIRS (CTA-pair schedule, where this CTA takes tile
+// 2 * pair + rank: qmul = 2, qadd = rank).
 struct SearchTileIter {
-    int item, step, items, nq, cps, nchunks;
+    int item, step, items, nq, cps, nchunks, qmul, qadd;
     int chunk = 0, chunk_end = 0, row_q = 0;
     __device__ __forceinline__ SearchTileIter(int first, int step_, int items_, int nq_, int cps_,
-                                              int nchunks_)
-        : item(first), step(step_), items(items_), nq(nq_), cps(cps_), nchunks(nchunks_) {}
+                                              int nchunks_, int qmul_ = 1, int qadd_ = 0)
+        : item(first), step(step_), items(items_), nq(nq_), cps(cps_), nchunks(nchunks_), qmul(qmul_), qadd(qadd_) {}
     __device__ __forceinline__ bool next(int& row_a, int& row_b) {
         while (chunk >= chunk_end) {
             if (item >= items) return false;
             const int split = item / nq;
-            row_q = (item % nq) * kBM;
+            row_q = ((item % nq) * qmul + qadd) * kBM;
             chunk = split * cps;
             chunk_end = min(chunk + cps, nchunks);
             item += step;
@@ -164,28 +173,46 @@ __device__ __forceinline__ void reg_insert(float (&s)[KR], int (&id)[KR], float 
 }
 
 // KR > 0: top-k lists in registers (k <= KR); KR == 0: lists in shared memory (k <= kMaxK).
-template <int kSStages, int KR>
+// kPair: clusters of two CTAs (tcgen05 cta_group::2) score 256 queries against each corpus chunk;
+// every CTA stages only half of the chunk (32 KB stages -> a deeper ring beside large lists, half
+// the L2 -> SM corpus traffic) and keeps the lists of its own 128 query rows. `nq` then counts
+// query-tile pairs.
+template <int kSStages, int KR, bool kPair>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                    const __grid_constant__ CUtensorMap tmap_c, float* __restrict__ part_scores,
                    int32_t* __restrict__ part_ids, int64_t Q, int64_t N, int D, int k, int nq, int cps,
                    int nchunks, int nsplit, int cbuf) {
-    using SM = PipeSmem<kSBN, kSStages>;
+    using SM = PipeSmem<kSBN, kSStages, 0, kPair ? 2 : 1>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     SM sm{smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)};
     const int warp = __shfl_sync(0xffffffff, threadIdx.x / 32, 0);
     const int lane = threadIdx.x & 31;
     const int kblocks = (D + kBK - 1) / kBK;
     const int items = nq * nsplit;
-    SearchTileIter it(static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), items, nq, cps, nchunks);
+    const int rank = kPair ? static_cast<int>(cluster_ctarank()) : 0;
+    const int item0 = kPair ? static_cast<int>(blockIdx.x) / 2 : static_cast<int>(blockIdx.x);
+    const int item_step = kPair ? static_cast<int>(gridDim.x) / 2 : static_cast<int>(gridDim.x);
+    SearchTileIter it(item0, item_step, items, nq, cps, nchunks, kPair ? 2 : 1, rank);
 
-    const uint32_t tmem_base = pipe_setup(sm, warp, &tmap_q, &tmap_c, 128);
+    uint32_t tmem_base;
+    if constexpr (kPair) tmem_base = pipe2_setup(sm, warp, &tmap_q, &tmap_c, 2 * 4);
+    else tmem_base = pipe_setup(sm, warp, &tmap_q, &tmap_c, 128);
 
     if (warp == 0) {
         // queries are re-read by every chunk -> keep in L2; the corpus streams through once per split
-        if (elect_one()) pipe_produce(sm, &tmap_q, &tmap_c, it, kblocks, kEvictLast, kEvictNormal);
+        if (elect_one()) {
+            if constexpr (kPair) pipe2_produce(sm, &tmap_q, &tmap_c, it, kblocks, rank, kEvictLast, kEvictNormal);
+            else pipe_produce(sm, &tmap_q, &tmap_c, it, kblocks, kEvictLast, kEvictNormal);
+        }
     } else if (warp == 1) {
-        if (elect_one()) pipe_mma<SM, false>(sm, tmem_base, it, kblocks);
+        if (elect_one()) {
+            if constexpr (kPair) {
+                if (rank == 0) pipe2_mma<SM, false>(sm, tmem_base, it, kblocks);
+            } else {
+                pipe_mma<SM, false>(sm, tmem_base, it, kblocks);
+            }
+        }
     } else {
         const int lane_grp = warp & 3;
         const int trow = lane_grp * 32 + lane;  // row of the 128-query tile owned by this thread
@@ -204,9 +231,9 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         int* cbi = cbi_all + trow * cstride;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        for (int item = item0; item < items; item += item_step) {
             const int split = item / nq;
-            const int qt = item % nq;
+            const int qt = kPair ? (item % nq) * 2 + rank : item % nq;
             const int c_begin = split * cps;
             const int c_end = min(c_begin + cps, nchunks);
             constexpr int KRA = KR > 0 ? KR : 1;
@@ -319,7 +346,12 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     tmem_ld_wait();
                     if (c0 + 32 == kSBN) {  // the whole accumulator has been read: hand the TMEM buffer back
                         tc_fence_before();
-                        mbar_arrive(sm.tmem_empty(acc));
+                        if constexpr (kPair) {  // one arrival per warp on the leader CTA's barrier
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_remote_cta(map_to_cta(smem_u32(sm.tmem_empty(acc)), 0));
+                        } else {
+                            mbar_arrive(sm.tmem_empty(acc));
+                        }
                     }
                     scan(r, c0);
                 }
@@ -352,7 +384,8 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             }
         }
     }
-    pipe_teardown(sm, warp, tmem_base);
+    if constexpr (kPair) pipe2_teardown(sm, warp, tmem_base);
+    else pipe_teardown(sm, warp, tmem_base);
 }
 
 // ----------------------------------------------------------------------------- k-way merge
@@ -809,7 +842,8 @@ int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int6
 
     CUtensorMap tq, tc;
     if (!make_tmap_bf16_k64(&tq, q, static_cast<uint64_t>(Q), static_cast<uint64_t>(D), static_cast<uint64_t>(D), kBM) ||
-        !make_tmap_bf16_k64(&tc, corpus, static_cast<uint64_t>(N), static_cast<uint64_t>(D), static_cast<uint64_t>(D), kSBN)) {
+        !make_tmap_bf16_k64(&tc, corpus, static_cast<uint64_t>(N), static_cast<uint64_t>(D), static_cast<uint64_t>(D),
+                            p.pair ? kSBN / 2 : kSBN)) {
         set_error("search: cuTensorMapEncodeTiled failed");
         return ARB_ERR_CUDA;
     }
@@ -826,18 +860,45 @@ int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int6
         const int slots = lk + (cbuf > 1 ? cbuf + 1 : cbuf);
         const int smem = ring_bytes + slots * kBM * 8 + 1024;
         ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        kern<<<p.grid, kSearchThreads, smem, stream>>>(tq, tc, part_scores, part_ids, Q, N, D, k, p.nq, p.cps,
-                                                       p.nchunks, p.nsplit, cbuf);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>(p.grid));
+        cfg.blockDim = dim3(kSearchThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = p.pair ? 2 : 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        ARB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tc, part_scores, part_ids, Q, N, D, k, p.nq, p.cps, p.nchunks,
+                                          p.nsplit, cbuf));
         return ARB_OK;
     };
-    constexpr int kRing4 = PipeSmem<kSBN, 4>::kExtraOffset, kRing3 = PipeSmem<kSBN, 3>::kExtraOffset,
-                  kRing2 = PipeSmem<kSBN, 2>::kExtraOffset;
-    static_assert((kSmemMax - 1024 - kRing4) / (kBM * 8) >= 33, "register-list kernels need a 32-candidate buffer");
     int lrc;
-    if (k <= 10) lrc = launch(search_topk_kernel<4, 10>, kRing4, 0, 32);
-    else if (k <= 16) lrc = launch(search_topk_kernel<4, 16>, kRing4, 0, 32);
-    else if (buffer_for(kRing3, k) >= 16) lrc = launch(search_topk_kernel<3, 0>, kRing3, k, buffer_for(kRing3, k));
-    else lrc = launch(search_topk_kernel<2, 0>, kRing2, k, buffer_for(kRing2, k));
+    if (p.pair) {
+        // 32 KB stages (query tile + half a corpus chunk per CTA): the deepest ring that leaves the
+        // lists and a >= 16-candidate buffer in place
+        constexpr int kP6 = PipeSmem<kSBN, 6, 0, 2>::kExtraOffset, kP5 = PipeSmem<kSBN, 5, 0, 2>::kExtraOffset,
+                      kP4 = PipeSmem<kSBN, 4, 0, 2>::kExtraOffset, kP3 = PipeSmem<kSBN, 3, 0, 2>::kExtraOffset,
+                      kP2 = PipeSmem<kSBN, 2, 0, 2>::kExtraOffset;
+        static_assert((kSmemMax - 1024 - kP6) / (kBM * 8) >= 33, "register-list kernels need a 32-candidate buffer");
+        if (k <= 10) lrc = launch(search_topk_kernel<6, 10, true>, kP6, 0, 32);
+        else if (k <= 16) lrc = launch(search_topk_kernel<6, 16, true>, kP6, 0, 32);
+        else if (buffer_for(kP5, k) >= 16) lrc = launch(search_topk_kernel<5, 0, true>, kP5, k, buffer_for(kP5, k));
+        else if (buffer_for(kP4, k) >= 16) lrc = launch(search_topk_kernel<4, 0, true>, kP4, k, buffer_for(kP4, k));
+        else if (buffer_for(kP3, k) >= 16) lrc = launch(search_topk_kernel<3, 0, true>, kP3, k, buffer_for(kP3, k));
+        else lrc = launch(search_topk_kernel<2, 0, true>, kP2, k, buffer_for(kP2, k));
+    } else {
+        constexpr int kRing4 = PipeSmem<kSBN, 4>::kExtraOffset, kRing3 = PipeSmem<kSBN, 3>::kExtraOffset,
+                      kRing2 = PipeSmem<kSBN, 2>::kExtraOffset;
+        static_assert((kSmemMax - 1024 - kRing4) / (kBM * 8) >= 33, "register-list kernels need a 32-candidate buffer");
+        if (k <= 10) lrc = launch(search_topk_kernel<4, 10, false>, kRing4, 0, 32);
+        else if (k <= 16) lrc = launch(search_topk_kernel<4, 16, false>, kRing4, 0, 32);
+        else if (buffer_for(kRing3, k) >= 16) lrc = launch(search_topk_kernel<3, 0, false>, kRing3, k, buffer_for(kRing3, k));
+        else lrc = launch(search_topk_kernel<2, 0, false>, kRing2, k, buffer_for(kRing2, k));
+    }
     if (lrc) return lrc;
     ARB_CHECK_CUDA(cudaGetLastError());
     return launch_merge_impl<int32_t>(part_scores, part_ids, p.nsplit, Q * k, Q * k, Q, k, id_offset, out_scores,

@@ -159,10 +159,10 @@ __device__ __forceinline__ void pipe_mma(const SM& sm, uint32_t tmem_base, TileI
 // tmem_full barriers of BOTH CTAs. Each CTA's epilogue drains its own 128 accumulator rows and
 // reports to the leader's tmem_empty barrier (one arrival per warp). Compared with two
 // independent CTAs this halves the B bytes staged per SM and per MMA, which buys a deeper ring.
-constexpr int kPairEpiArrivals = 2 * 8;  // 2 CTAs x 8 epilogue warps
-
+// epi_arrivals = arrivals per accumulator hand-back: 2 CTAs x epilogue warps per CTA
 template <class SM>
-__device__ __forceinline__ uint32_t pipe2_setup(const SM& sm, int warp, const void* tmap_a, const void* tmap_b) {
+__device__ __forceinline__ uint32_t pipe2_setup(const SM& sm, int warp, const void* tmap_a, const void* tmap_b,
+                                                uint32_t epi_arrivals) {
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(tmap_a);
         tma_prefetch_desc(tmap_b);
@@ -172,7 +172,7 @@ __device__ __forceinline__ uint32_t pipe2_setup(const SM& sm, int warp, const vo
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(sm.tmem_full(s), 1);
-            mbar_init(sm.tmem_empty(s), kPairEpiArrivals);
+            mbar_init(sm.tmem_empty(s), epi_arrivals);
         }
         for (int s = 0; s < 4; ++s) mbar_init(sm.aux(s), 1);
         fence_barrier_init();

@@ -122,6 +122,11 @@ int arb_topk_search(const void* queries_dev, const void* corpus_dev, int32_t dty
 /* Merge G sorted per-shard lists (e.g. the all-gathered [G,Q,k] of a row-sharded corpus). */
 int arb_topk_merge(const float* scores_dev, const int64_t* ids_dev, int32_t G, int64_t Q, int32_t k,
                    float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+/* Schedule of arb_topk_search (process-wide; for tests and benchmarks): 0 = auto, 1 = one CTA per
+ * 128-query tile, 2 = CTA pairs (cta_group::2) scoring 256 queries per corpus chunk. Auto uses
+ * pairs whenever there is more than one query tile. The workspace size depends on the mode: query it
+ * after setting the mode. */
+int arb_set_search_mode(int32_t mode);
 /* Row-sharded search moves each rank's result in ONE all-gather: a record is the rank's [Q,k]
  * float32 scores followed, at arb_topk_record_ids_offset (8-byte aligned), by its [Q,k] int64 ids —
  * pass those two addresses to arb_topk_search as out_scores_dev / out_ids_dev. arb_topk_merge_records

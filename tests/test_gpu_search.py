@@ -88,6 +88,30 @@ def test_many_duplicates_buffered_lists(cuda, k):
     assert rep["ok"], rep
 
 
+@pytest.mark.parametrize("bf16", [True, False])
+@pytest.mark.parametrize("shape", [(129, 5000, 10), (300, 20000, 16), (257, 20000, 100), (1000, 30000, 10), (640, 9000, 64),
+                                   (130, 3000, 128), (5, 300, 10)])
+def test_pair_schedule_equals_single_cta(cuda, bf16, shape):
+    """The CTA-pair schedule (tcgen05 cta_group::2, two query tiles per corpus chunk; auto for
+    Q > 128) and the single-CTA schedule must return identical ids and scores — odd tile counts
+    (the pair's second CTA has no queries), every list type, ragged N — and meet the oracle."""
+    from arxiv_rag_b200 import _lib
+
+    Q, N, k = shape
+    c = so.synthetic_unit_rows(N, 768, seed=2, bf16=bf16, plant_ties=True)
+    q = so.synthetic_unit_rows(Q, 768, seed=3, bf16=bf16)
+    out = []
+    try:
+        for mode in (1, 2):
+            _lib.check(_lib.lib().arb_set_search_mode(mode))
+            out.append(_run(q, c, k, bf16, id_offset=7))
+    finally:
+        _lib.check(_lib.lib().arb_set_search_mode(0))
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][0], out[1][0])
+    rep = so.check_topk(out[1][0], out[1][1], q, c, k, tol=TOL, id_offset=7)
+    assert rep["ok"], rep
+
+
 def test_cfg1_reference_case(cuda):
     """BASELINE configs[0] search half: 1k queries over 10k rows, top-10, fp32."""
     c = so.synthetic_unit_rows(10_000, 768, seed=0)
