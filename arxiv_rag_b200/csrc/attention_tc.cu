@@ -1,6 +1,6 @@
 // tcgen05/TMEM self-attention for the MPNet encoder (64 <= S <= 384, head dim 64):
 //   softmax(q.k^T/8 + rel_bias[h][j-i] + mask) . v   per (sequence, head)
-// Same contract as attention.cu (modeling_mpnet.py:162-177, :324-360; mask of
+// Same contract as attention_mma.cu (modeling_mpnet.py:162-177, :324-360; mask of
 // modeling_utils.py:936-947); this is the tensor-core version the encode path uses.
 //
 // CTA c serves head c % heads for sequences c / heads, + ngroups, ... (one persistent CTA per SM;
