@@ -252,3 +252,21 @@ def test_errors_raise(cuda, full_model):
     with pytest.raises(ArbError):
         enc.encode_tokens(ids, ids)  # B*S exceeds the handle's max_tokens
     enc.close()
+
+
+def test_full_size_batch_properties(cuda, full_model):
+    """BASELINE configs[1] step size (1024 chunks x 384 tokens, bf16): the oracle needs minutes for it,
+    so check size-independent properties — unit-norm finite rows, and every row equal to the same row
+    encoded in a 64-row batch (a row's arithmetic does not depend on its batch; the spot-checked
+    rows also meet the oracle bar)."""
+    arch, sd, model = full_model
+    ids, mask = eo.synthetic_tokens(1024, 384, seed=5, full_length=True)
+    enc = _encoder(arch, sd, "bf16", max_batch=1024, max_seq=384)
+    big = enc.encode((ids, mask), batch_size=1024, normalize_embeddings=True)
+    assert big.shape == (1024, 768) and np.isfinite(big).all()
+    assert np.allclose(np.linalg.norm(big, axis=1), 1.0, atol=1e-5)
+    small = enc.encode((ids[100:164], mask[100:164]), batch_size=64, normalize_embeddings=True)
+    assert np.abs(big[100:164] - small).max() < 1e-6
+    ref = eo.oracle_encode(model, ids[:4], mask[:4], batch_size=4)
+    assert _cos(big[:4], ref).min() >= COS_TOL
+    enc.close()

@@ -254,3 +254,50 @@ def test_argument_errors(cuda):
         idx.search(torch.zeros(2, 64, dtype=torch.bfloat16), k=5)
     s, i = idx.search(torch.zeros(0, 768, dtype=torch.bfloat16), k=5)
     assert tuple(s.shape) == (0, 5)
+
+
+# ---------------------------------------------------------------- BASELINE full size (configs[1]/[3] corpus): properties
+def test_full_size_5m_corpus_properties(cuda):
+    """5 M x 768 bf16 (the BASELINE search corpus, 7.7 GB): the oracle cannot brute-force it in test
+    time, so check size-independent properties — (a) 8 row shards + record merge == unsharded,
+    (b) planted rows are found at rank 0 with score 1 and an exact duplicate pair comes back in
+    ascending-id order, (c) returned scores are the fp32 dot products of the returned rows,
+    (d) both schedules (single CTA / CTA pair) agree bit for bit."""
+    from arxiv_rag_b200 import _lib
+
+    N, Q, k, G = 5_000_000, 300, 10, 8
+    g = torch.Generator(device="cuda").manual_seed(11)
+    c = torch.empty((N, 768), device=cuda, dtype=torch.bfloat16)
+    for s0 in range(0, N, 500_000):
+        c[s0:s0 + 500_000] = torch.nn.functional.normalize(torch.randn(500_000, 768, device=cuda, generator=g), dim=1).to(torch.bfloat16)
+    q = torch.nn.functional.normalize(torch.randn(Q, 768, device=cuda, generator=g), dim=1).to(torch.bfloat16)
+    planted = torch.tensor([0, 1_234_567, 2_500_000, 4_999_999], device=cuda)
+    q[:4] = c[planted]
+    c[3_333_333] = c[1_234_567]  # exact duplicate of a planted row, in another shard
+    index = S.CorpusIndex(c)
+    fs, fi = index.search(q, k)
+    assert fi[0, 0].item() == 0 and fi[2, 0].item() == 2_500_000 and fi[3, 0].item() == 4_999_999
+    assert fi[1, :2].tolist() == [1_234_567, 3_333_333] and fs[1, 0].item() == fs[1, 1].item()
+    assert (fs[:4, 0] - 1.0).abs().max().item() < 1e-2  # bf16 unit rows: |row|^2 within bf16 rounding of 1
+    assert (fs[:, :-1] >= fs[:, 1:]).all()
+    chk = (q[:32].float()[:, None, :] * c[fi[:32]].float()).sum(-1)
+    assert (chk - fs[:32]).abs().max().item() < TOL
+    # (a) shards
+    rec, off = int(_lib.lib().arb_topk_record_bytes(Q, k)), int(_lib.lib().arb_topk_record_ids_offset(Q, k))
+    gathered = torch.zeros(G * rec, dtype=torch.uint8, device=cuda)
+    for r in range(G):
+        lo, hi = S.shard_bounds(N, G, r)
+        ls = gathered[r * rec:r * rec + Q * k * 4].view(torch.float32).view(Q, k)
+        li = gathered[r * rec + off:r * rec + off + Q * k * 8].view(torch.int64).view(Q, k)
+        S.CorpusIndex(c[lo:hi], id_offset=lo).search(q, k, out_scores=ls, out_ids=li)
+    ms = torch.empty((Q, k), dtype=torch.float32, device=cuda)
+    mi = torch.empty((Q, k), dtype=torch.int64, device=cuda)
+    _lib.check(_lib.lib().arb_topk_merge_records(_lib.ptr(gathered), G, Q, k, _lib.ptr(ms), _lib.ptr(mi), _lib.current_stream()))
+    assert torch.equal(mi, fi) and torch.equal(ms, fs)
+    # (d) schedules
+    try:
+        _lib.check(_lib.lib().arb_set_search_mode(1))
+        s1, i1 = index.search(q, k)
+        assert torch.equal(i1, fi) and torch.equal(s1, fs)
+    finally:
+        _lib.check(_lib.lib().arb_set_search_mode(0))
