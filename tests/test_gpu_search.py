@@ -90,7 +90,7 @@ def test_many_duplicates_buffered_lists(cuda, k):
 
 @pytest.mark.parametrize("bf16", [True, False])
 @pytest.mark.parametrize("shape", [(129, 5000, 10), (300, 20000, 16), (257, 20000, 100), (1000, 30000, 10), (640, 9000, 64),
-                                   (130, 3000, 128), (5, 300, 10)])
+                                   (130, 3000, 128), (5, 300, 10), (200, 50, 10), (300, 129, 5), (257, 7, 10)])
 def test_pair_schedule_equals_single_cta(cuda, bf16, shape):
     """The CTA-pair schedule (tcgen05 cta_group::2, two query tiles per corpus chunk; auto for
     Q > 128) and the single-CTA schedule must return identical ids and scores — odd tile counts
