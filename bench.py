@@ -422,6 +422,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "b200":
+        args.warmup = max(args.warmup, 3)  # timing rule: at least 3 untimed warm-up steps
     with _StdoutGuard():
         result = run_reference(args) if args.impl == "reference" else run_b200(args)
     if result is not None:  # rank 0 only: the one JSON line, alone on stdout
