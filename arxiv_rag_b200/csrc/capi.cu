@@ -413,7 +413,8 @@ int arb_topk_search(const void* queries_dev, const void* corpus_dev, int32_t dty
     return ARB_ERR_INVALID;
 }
 
-int arb_topk_search_launches(int32_t dtype) { return dtype == ARB_DTYPE_F32 ? 5 : 2; }
+// search kernel + split merge (+ the query pad copy when Q is not a whole number of tiles; + split x2 and re-score for fp32)
+int arb_topk_search_launches(int32_t dtype) { return dtype == ARB_DTYPE_F32 ? 6 : 3; }
 
 int arb_topk_merge(const float* scores_dev, const int64_t* ids_dev, int32_t G, int64_t Q, int32_t k,
                    float* out_scores_dev, int64_t* out_ids_dev, void* stream) {

@@ -812,12 +812,29 @@ int launch_topk_exchange_merge(const void* local_record, void* const* peer_bufs_
 // ----------------------------------------------------------------------------- bf16 search
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// A query tile that hangs over the end of the query matrix is filled in by TMA's out-of-bounds
+// path, and that path is slow: measured on a 5 M-row corpus, Q=1 takes 1.65 ms per pass with the
+// hardware zero fill and 1.20 ms (6.4 TB/s, 98 % of the HBM peak) when the same zeros are real rows.
+// So queries are copied into a buffer padded to whole tiles whenever Q is not a multiple of the
+// tile (and small enough for the copy not to matter).
+static int64_t padded_queries(int64_t Q, bool pair) {
+    const int64_t tile = pair ? 2 * kBM : kBM;
+    return (Q % tile != 0 && Q <= 16384) ? (Q + tile - 1) / tile * tile : 0;  // 0: use the caller's matrix
+}
+
+__global__ void __launch_bounds__(256)
+pad_queries_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t valid, int64_t total) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        dst[i] = i < valid ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+}
+
 size_t search_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
-    (void)D;
-    if (Q <= 0 || N <= 0 || k <= 0) return 0;
+    if (Q <= 0 || N <= 0 || k <= 0 || D <= 0) return 0;
     const SearchPlan p = make_plan(Q, N, k);
     const size_t per = static_cast<size_t>(p.nsplit) * Q * k;
-    return align_up(per * 4, 256) + align_up(per * 4, 256);
+    const size_t pad = static_cast<size_t>(padded_queries(Q, p.pair)) * D * 2;
+    return align_up(per * 4, 256) + align_up(per * 4, 256) + align_up(pad, 256);
 }
 
 int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int64_t Q, int64_t N,
@@ -840,8 +857,17 @@ int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int6
     float* part_scores = reinterpret_cast<float*>(workspace);
     int32_t* part_ids = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) + align_up(per * 4, 256));
 
+    const int64_t Qp = padded_queries(Q, p.pair);
+    if (Qp > 0) {  // whole query tiles only: see padded_queries
+        __nv_bfloat16* qpad = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + 2 * align_up(per * 4, 256));
+        const int64_t total = Qp * D / 8, valid = Q * D / 8;
+        const int blocks = static_cast<int>(total < 148ll * 8 * 256 ? (total + 255) / 256 : 148 * 8);
+        pad_queries_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(q), reinterpret_cast<uint4*>(qpad), valid, total);
+        ARB_CHECK_CUDA(cudaGetLastError());
+        q = qpad;
+    }
     CUtensorMap tq, tc;
-    if (!make_tmap_bf16_k64(&tq, q, static_cast<uint64_t>(Q), static_cast<uint64_t>(D), static_cast<uint64_t>(D), kBM) ||
+    if (!make_tmap_bf16_k64(&tq, q, static_cast<uint64_t>(Qp > 0 ? Qp : Q), static_cast<uint64_t>(D), static_cast<uint64_t>(D), kBM) ||
         !make_tmap_bf16_k64(&tc, corpus, static_cast<uint64_t>(N), static_cast<uint64_t>(D), static_cast<uint64_t>(D),
                             p.pair ? kSBN / 2 : kSBN)) {
         set_error("search: cuTensorMapEncodeTiled failed");

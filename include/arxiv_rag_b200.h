@@ -154,7 +154,8 @@ int arb_topk_exchange_merge(const void* local_record_dev, const void* peer_bufs_
 /* out[i] = cos(emb[i], emb[i-1]) for fp32 rows [n, D] (out[0] = 1): the adjacent-sentence similarity
  * TextChunker._chunk_semantic computes with _cosine_similarity (text_processor.py:1547-1561, :1601-1605). */
 int arb_adjacent_cosine(const float* emb_dev, int64_t n, int32_t D, float* out_dev, void* stream);
-/* Number of kernel launches one arb_topk_search call enqueues. */
+/* Upper bound on the kernel launches one arb_topk_search call enqueues (the query pad copy is skipped
+ * when Q is a whole number of query tiles). */
 int arb_topk_search_launches(int32_t dtype);
 
 /* ------------------------------------------------------------------------------------------
