@@ -17,6 +17,7 @@ LIB_PATH = Path(os.environ.get("ARB_LIB_PATH") or
 ARB_DTYPE_F32 = 0
 ARB_DTYPE_BF16 = 1
 ARB_DTYPE_F16 = 2
+ARB_DTYPE_BF16_WF16 = 3  # bf16 activations x fp16 weights: the shipped "bf16" mode
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 
 
@@ -75,6 +76,8 @@ SIGNATURES = {
     "arb_mpnet_device_bytes": (_I64, [_VP]),
     "arb_mpnet_encode": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP]),
     "arb_mpnet_launches_per_encode": (C.c_int, [_VP]),
+    "arb_mpnet_status": (C.c_int, [_VP]),
+    "arb_mpnet_short_seq": (C.c_int, [_VP]),
     "arb_mpnet_relative_bucket": (C.c_int, [_I32, _I32, _I32]),
     "arb_topk_search_workspace_bytes": (_SZ, [_I32, _I64, _I64, _I32, _I32]),
     "arb_topk_search": (C.c_int, [_VP, _VP, _I32, _I64, _I64, _I32, _I32, _VP, _VP, _I64, _VP, _SZ, _VP]),
@@ -97,8 +100,6 @@ SIGNATURES = {
     "arb_adjacent_cosine": (C.c_int, [_VP, _I64, _I32, _VP, _VP]),
     "arb_gemm16": (C.c_int, [_VP, _I64, _VP, _I64, _VP, _I64, _VP, _VP, _I64, _I64, _I32, _I32, _I32, _I32, _VP]),
     "arb_gemm16_f32out": (C.c_int, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP]),
-    "arb_gemm16_residual_ln": (C.c_int, [_VP, _I64, _VP, _I64, _VP, _I64, _VP, _VP, _I64, _VP, _VP, _F, _I64, _I32, _I32,
-                                         _I32, _VP]),
     "arb_embed_layernorm": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F, _I32, _VP]),
     "arb_layernorm16": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _F, _I32, _VP]),
     "arb_attention16": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),

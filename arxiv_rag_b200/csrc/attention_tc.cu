@@ -93,7 +93,7 @@ __host__ __device__ inline AtLayout at_layout(int Kh, int nqt) {
     L.mask_off = L.bias_off + 2 * (L.nbias + 2) * 4;  // two copies (shift 0 / shift 1), padded
     L.exch_off = L.mask_off + 2 * (2 * Kh) * 4;       // one mask table per softmax group
     L.red_off = L.exch_off + 2 * 2 * kAtQT * 8;       // [parity][half][row] (c, l)
-    L.bar_off = (L.red_off + 16 * 4 + 7) & ~7;
+    L.bar_off = (L.red_off + 32 * 4 + 7) & ~7;
     L.total = L.bar_off + 16 * 8 + 16;
     return L;
 }
@@ -200,21 +200,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     float* T1 = T0 + L.nbias + 2;
     float* red = reinterpret_cast<float*>(sm + L.red_off);
     {
-        float bm = -INFINITY;
+        float bm = -INFINITY, bn = INFINITY;
         for (int e = threadIdx.x; e < L.nbias + 2; e += kAtThreads) {
             const int rel = e - OFF;
             float v = 0.f;
             if (e < L.nbias && rel > -S && rel < S) {
                 v = rel_bias[static_cast<int64_t>(h) * (2 * max_rel - 1) + rel + (max_rel - 1)] * kAtLog2e;
                 bm = fmaxf(bm, v);
+                bn = fminf(bn, v);
             }
             T0[e] = v;
             if (e >= 1) T1[e - 1] = v;
         }
         if (threadIdx.x == 0) T1[L.nbias + 1] = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffff, bm, o));
-        if (lane == 0) red[warp] = bm;
+        for (int o = 16; o > 0; o >>= 1) {
+            bm = fmaxf(bm, __shfl_xor_sync(0xffffffff, bm, o));
+            bn = fminf(bn, __shfl_xor_sync(0xffffffff, bn, o));
+        }
+        if (lane == 0) {
+            red[warp] = bm;
+            red[16 + warp] = bn;
+        }
     }
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&tmap_q);
@@ -240,9 +247,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    float bmax = red[0];
+    float bmax = red[0], bmin = red[16];
 #pragma unroll
-    for (int w = 1; w < kAtThreads / 32; ++w) bmax = fmaxf(bmax, red[w]);
+    for (int w = 1; w < kAtThreads / 32; ++w) {
+        bmax = fmaxf(bmax, red[w]);
+        bmin = fminf(bmin, red[16 + w]);
+    }
+    // The softmax shift is the bound c = max(raw) * scale + max(bias) >= the true row maximum; the
+    // true maximum sits at most D = max(bias) - min(bias) below it. bf16 probabilities keep the fp32
+    // exponent range, but fp16 ones would drift into subnormals once D exceeds 14 (a trained
+    // relative-position table spreads over many log2 units). fp16 mode therefore lowers the shift
+    // by min(D, 15): p <= 2^15 still fits fp16, the row maximum stays >= 2^-14 for D up to 29, and
+    // both key halves use the same constant, so the combine is unchanged.
+    if (kF16) bmax -= fminf(bmax - bmin, 15.f);
 
     if (warp == 0) {
         // ===================== TMA producer =====================

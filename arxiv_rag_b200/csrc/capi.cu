@@ -26,6 +26,15 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+// public 16-bit dtype code -> operand formats of a launch (kernels.h FMT_*)
+static int dtype16(int32_t dtype, int* fmt) {
+    ARB_REQUIRE(dtype == ARB_DTYPE_BF16 || dtype == ARB_DTYPE_F16 || dtype == ARB_DTYPE_BF16_WF16,
+                "dtype %d must be ARB_DTYPE_BF16, ARB_DTYPE_F16 or ARB_DTYPE_BF16_WF16", dtype);
+    *fmt = dtype == ARB_DTYPE_F16 ? (FMT_ACT_F16 | FMT_W_F16) : dtype == ARB_DTYPE_BF16_WF16 ? FMT_W_F16 : 0;
+    return ARB_OK;
+}
+
+
 // ---- MPNetEncoder.relative_position_bucket (modeling_mpnet.py:343-360), float32 like torch.
 static int relative_bucket(int relative_position, int num_buckets, int max_distance) {
     int n = -relative_position;
@@ -64,8 +73,14 @@ struct Mpnet {
     float* rel_bias = nullptr;  // [heads, 2*max_seq-1], entry r <-> j-i = r-(max_seq-1)
     std::vector<LayerDev> layers;
     h16 *h = nullptr, *h1 = nullptr, *tmp = nullptr, *ctx = nullptr, *qkv = nullptr, *ffn = nullptr;
-    bool fp16 = false;
-    bool fuse_ln = false;  // residual GEMMs carry the post-LN in their epilogue (cluster kernel)
+    int fmt = 0;           // FMT_ACT_F16 | FMT_W_F16 (kernels.h): 16-bit formats of activations / weights
+    // compute_dtype ARB_DTYPE_BF16_WF16: batches padded to fewer than kShortSeq tokens run with
+    // fp16 activations (same fp16 weights, same buffers). A row of a few tokens has no mean-pool
+    // averaging over its bf16 activation noise and cannot reach cosine 0.9999 otherwise
+    // (tools/rounding_budget.py); such values are far inside the fp16 range after the LayerNorms.
+    bool short_f16 = false;
+    int* status_host = nullptr;  // host-mapped status word [0]=error, [1]=token id, [2]=token index
+    int* status_dev = nullptr;
     // LayerNorm folded into the neighbouring GEMMs: producers write pre-LN rows + row partials,
     // consumers carry gamma in their weights and finish the normalisation in the epilogue.
     bool fold_ln = false;
@@ -90,7 +105,7 @@ struct Mpnet {
     int upload16(h16* dst, const float* src, size_t count) {
         ARB_REQUIRE(src != nullptr, "mpnet_create: missing weight matrix");
         std::vector<h16> tmpv(count);
-        if (fp16) {
+        if (fmt_w_f16(fmt)) {
             for (size_t i = 0; i < count; ++i) tmpv[i] = __half_as_ushort(__float2half_rn(src[i]));
         } else {
             for (size_t i = 0; i < count; ++i) tmpv[i] = __bfloat16_as_ushort(__float2bfloat16_rn(src[i]));
@@ -110,7 +125,7 @@ struct Mpnet {
             for (size_t k = 0; k < K; ++k) {
                 const float wf = w[n * K + k] * gamma[k];
                 float back;
-                if (fp16) {
+                if (fmt_w_f16(fmt)) {
                     const __half hv = __float2half_rn(wf);
                     t16[n * K + k] = __half_as_ushort(hv);
                     back = __half2float(hv);
@@ -132,6 +147,7 @@ struct Mpnet {
     }
     ~Mpnet() {
         for (void* p : allocs) cudaFree(p);
+        if (status_host) cudaFreeHost(status_host);
     }
 };
 
@@ -215,15 +231,19 @@ static int mpnet_build(Mpnet* m, const ArbMpnetWeights* w) {
     return ARB_OK;
 }
 
+constexpr int kShortSeq = 32;
+
 static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B, int S, float* out,
                         cudaStream_t st) {
     const ArbMpnetConfig& c = m->cfg;
     const int H = c.hidden_size, I = c.intermediate_size;
     const int64_t T = static_cast<int64_t>(B) * S;
+    const int fmt = m->fmt | ((m->short_f16 && S < kShortSeq) ? FMT_ACT_F16 : 0);
+    const bool a16 = fmt_act_f16(fmt);
     int rc;
     if ((rc = launch_embed_ln(ids, m->word_emb, m->pos_emb, m->emb_g, m->emb_b, m->h, B, S, H,
                               c.vocab_size, c.max_position_embeddings, c.pad_token_id, c.position_mode,
-                              c.layer_norm_eps, m->fp16, st)))
+                              c.layer_norm_eps, a16, m->status_dev, st)))
         return rc;
     if (m->fold_ln) {
         // No LayerNorm passes between the GEMMs: x (pre-LN, in `tmp`) and y (pre-LN, in `h1`) travel
@@ -236,62 +256,53 @@ static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B
             const LayerDev& d = m->layers[l];
             LnFoldArgs fq = f, fo = f, fu = f, fd = f;
             if (l == 0) {  // the embedding LayerNorm output is already normalised
-                if ((rc = launch_gemm16(m->h, H, d.w_qkv, H, m->qkv, 3 * H, d.b_qkv, nullptr, 0, T, 3 * H, H, EPI_BIAS, m->fp16, st))) return rc;
+                if ((rc = launch_gemm16(m->h, H, d.w_qkv, H, m->qkv, 3 * H, d.b_qkv, nullptr, 0, T, 3 * H, H, EPI_BIAS, fmt, st))) return rc;
             } else {
                 fq.colsum = d.c_qkv;
                 fq.stats_in = m->stats_x;
-                if ((rc = launch_gemm16_fold(m->tmp, H, d.w_qkv, H, m->qkv, 3 * H, d.b_qkv, nullptr, 0, T, 3 * H, H, EPI_LNIN_BIAS, fq, m->fp16, st))) return rc;
+                if ((rc = launch_gemm16_fold(m->tmp, H, d.w_qkv, H, m->qkv, 3 * H, d.b_qkv, nullptr, 0, T, 3 * H, H, EPI_LNIN_BIAS, fq, fmt, st))) return rc;
             }
-            if ((rc = launch_attention(m->qkv, m->rel_bias, m->max_seq, mask, m->ctx, B, S, c.num_heads, H / c.num_heads, m->fp16, 0, st))) return rc;
+            if ((rc = launch_attention(m->qkv, m->rel_bias, m->max_seq, mask, m->ctx, B, S, c.num_heads, H / c.num_heads, a16, 0, st))) return rc;
             // y = ctx Wo^T + bo + LN2_{l-1}(x)   (layer 0: + h), row partials of y
             fo.stats_out = m->stats_y;
             if (l == 0) {
-                if ((rc = launch_gemm16_fold(m->ctx, H, d.w_o, H, m->h1, H, d.b_o, m->h, H, T, H, H, EPI_BIAS_RES_STATS, fo, m->fp16, st))) return rc;
+                if ((rc = launch_gemm16_fold(m->ctx, H, d.w_o, H, m->h1, H, d.b_o, m->h, H, T, H, H, EPI_BIAS_RES_STATS, fo, fmt, st))) return rc;
             } else {
                 fo.gamma = m->layers[l - 1].ln2_g;
                 fo.beta = m->layers[l - 1].ln2_b;
                 fo.stats_in = m->stats_x;
-                if ((rc = launch_gemm16_fold(m->ctx, H, d.w_o, H, m->h1, H, d.b_o, m->tmp, H, T, H, H, EPI_BIAS_LNRES_STATS, fo, m->fp16, st))) return rc;
+                if ((rc = launch_gemm16_fold(m->ctx, H, d.w_o, H, m->h1, H, d.b_o, m->tmp, H, T, H, H, EPI_BIAS_LNRES_STATS, fo, fmt, st))) return rc;
             }
             // ffn = gelu(LN1(y) W1^T + b1)
             fu.colsum = d.c_in;
             fu.stats_in = m->stats_y;
-            if ((rc = launch_gemm16_fold(m->h1, H, d.w_in, H, m->ffn, I, d.b_in, nullptr, 0, T, I, H, EPI_LNIN_BIAS_GELU, fu, m->fp16, st))) return rc;
+            if ((rc = launch_gemm16_fold(m->h1, H, d.w_in, H, m->ffn, I, d.b_in, nullptr, 0, T, I, H, EPI_LNIN_BIAS_GELU, fu, fmt, st))) return rc;
             // x = ffn W2^T + b2 + LN1(y), row partials of x
             fd.gamma = d.ln1_g;
             fd.beta = d.ln1_b;
             fd.stats_in = m->stats_y;
             fd.stats_out = m->stats_x;
-            if ((rc = launch_gemm16_fold(m->ffn, I, d.w_out, I, m->tmp, H, d.b_out, m->h1, H, T, H, I, EPI_BIAS_LNRES_STATS, fd, m->fp16, st))) return rc;
+            if ((rc = launch_gemm16_fold(m->ffn, I, d.w_out, I, m->tmp, H, d.b_out, m->h1, H, T, H, I, EPI_BIAS_LNRES_STATS, fd, fmt, st))) return rc;
         }
         const LayerDev& last = m->layers[c.num_layers - 1];
-        if ((rc = launch_layernorm(m->tmp, last.ln2_g, last.ln2_b, m->h, T, H, c.layer_norm_eps, m->fp16, st))) return rc;
-        return launch_pool_normalize(m->h, mask, out, B, S, H, m->fp16, st);
+        if ((rc = launch_layernorm(m->tmp, last.ln2_g, last.ln2_b, m->h, T, H, c.layer_norm_eps, a16, st))) return rc;
+        return launch_pool_normalize(m->h, mask, out, B, S, H, a16, st);
     }
     for (int l = 0; l < c.num_layers; ++l) {
         const LayerDev& d = m->layers[l];
         // q,k,v projections as one [T,H] x [3H,H]^T GEMM (modeling_mpnet.py:145-159)
-        if ((rc = launch_gemm16(m->h, H, d.w_qkv, H, m->qkv, 3 * H, d.b_qkv, nullptr, 0, T, 3 * H, H, EPI_BIAS, m->fp16, st))) return rc;
+        if ((rc = launch_gemm16(m->h, H, d.w_qkv, H, m->qkv, 3 * H, d.b_qkv, nullptr, 0, T, 3 * H, H, EPI_BIAS, fmt, st))) return rc;
         // softmax(qk^T/8 + position_bias + mask) v (:162-177)
-        if ((rc = launch_attention(m->qkv, m->rel_bias, m->max_seq, mask, m->ctx, B, S, c.num_heads, H / c.num_heads, m->fp16, 0, st))) return rc;
-        // o-projection + residual + post-LN (:183, :210): one cluster kernel when H is a multiple of
-        // 256 (row statistics exchanged through DSMEM), else GEMM then a LayerNorm pass
-        if (m->fuse_ln) {
-            if ((rc = launch_gemm16_ln(m->ctx, H, d.w_o, H, m->h1, H, d.b_o, m->h, H, d.ln1_g, d.ln1_b, c.layer_norm_eps, T, H, H, m->fp16, st))) return rc;
-        } else {
-            if ((rc = launch_gemm16(m->ctx, H, d.w_o, H, m->tmp, H, d.b_o, m->h, H, T, H, H, EPI_BIAS_RESIDUAL, m->fp16, st))) return rc;
-            if ((rc = launch_layernorm(m->tmp, d.ln1_g, d.ln1_b, m->h1, T, H, c.layer_norm_eps, m->fp16, st))) return rc;
-        }
-        // FFN: GELU(erf) fused in the up-projection epilogue (:225-228), residual + post-LN in the down (:239-243)
-        if ((rc = launch_gemm16(m->h1, H, d.w_in, H, m->ffn, I, d.b_in, nullptr, 0, T, I, H, EPI_BIAS_GELU, m->fp16, st))) return rc;
-        if (m->fuse_ln) {
-            if ((rc = launch_gemm16_ln(m->ffn, I, d.w_out, I, m->h, H, d.b_out, m->h1, H, d.ln2_g, d.ln2_b, c.layer_norm_eps, T, H, I, m->fp16, st))) return rc;
-        } else {
-            if ((rc = launch_gemm16(m->ffn, I, d.w_out, I, m->tmp, H, d.b_out, m->h1, H, T, H, I, EPI_BIAS_RESIDUAL, m->fp16, st))) return rc;
-            if ((rc = launch_layernorm(m->tmp, d.ln2_g, d.ln2_b, m->h, T, H, c.layer_norm_eps, m->fp16, st))) return rc;
-        }
+        if ((rc = launch_attention(m->qkv, m->rel_bias, m->max_seq, mask, m->ctx, B, S, c.num_heads, H / c.num_heads, a16, 0, st))) return rc;
+        // o-projection + residual (:183), then the post-LN (:210) as a LayerNorm pass
+        if ((rc = launch_gemm16(m->ctx, H, d.w_o, H, m->tmp, H, d.b_o, m->h, H, T, H, H, EPI_BIAS_RESIDUAL, fmt, st))) return rc;
+        if ((rc = launch_layernorm(m->tmp, d.ln1_g, d.ln1_b, m->h1, T, H, c.layer_norm_eps, a16, st))) return rc;
+        // FFN: GELU fused in the up-projection epilogue (:225-228), residual in the down-projection (:239-243)
+        if ((rc = launch_gemm16(m->h1, H, d.w_in, H, m->ffn, I, d.b_in, nullptr, 0, T, I, H, EPI_BIAS_GELU, fmt, st))) return rc;
+        if ((rc = launch_gemm16(m->ffn, I, d.w_out, I, m->tmp, H, d.b_out, m->h1, H, T, H, I, EPI_BIAS_RESIDUAL, fmt, st))) return rc;
+        if ((rc = launch_layernorm(m->tmp, d.ln2_g, d.ln2_b, m->h, T, H, c.layer_norm_eps, a16, st))) return rc;
     }
-    return launch_pool_normalize(m->h, mask, out, B, S, H, m->fp16, st);
+    return launch_pool_normalize(m->h, mask, out, B, S, H, a16, st);
 }
 
 }  // namespace arb
@@ -301,7 +312,7 @@ using namespace arb;
 extern "C" {
 
 const char* arb_last_error(void) { return get_error(); }
-int arb_abi_version(void) { return 1; }
+int arb_abi_version(void) { return 2; }
 
 int arb_mpnet_relative_bucket(int32_t relative_position, int32_t num_buckets, int32_t max_distance) {
     return relative_bucket(relative_position, num_buckets, max_distance);
@@ -319,8 +330,9 @@ int arb_mpnet_create(const ArbMpnetConfig* cfg, const ArbMpnetWeights* weights, 
                 cfg->position_mode);
     ARB_REQUIRE(cfg->hidden_size % 128 == 0 && cfg->hidden_size <= 1024, "mpnet_create: hidden size %d unsupported", cfg->hidden_size);
     ARB_REQUIRE(cfg->intermediate_size % 32 == 0, "mpnet_create: intermediate size %d unsupported", cfg->intermediate_size);
-    ARB_REQUIRE(cfg->compute_dtype == ARB_DTYPE_BF16 || cfg->compute_dtype == ARB_DTYPE_F16,
-                "mpnet_create: compute_dtype %d must be ARB_DTYPE_BF16 or ARB_DTYPE_F16", cfg->compute_dtype);
+    ARB_REQUIRE(cfg->compute_dtype == ARB_DTYPE_BF16 || cfg->compute_dtype == ARB_DTYPE_F16 ||
+                    cfg->compute_dtype == ARB_DTYPE_BF16_WF16,
+                "mpnet_create: compute_dtype %d must be ARB_DTYPE_BF16_WF16, ARB_DTYPE_F16 or ARB_DTYPE_BF16", cfg->compute_dtype);
     ARB_REQUIRE(cfg->num_layers > 0 && cfg->vocab_size > 0 && cfg->max_position_embeddings > 2,
                 "mpnet_create: bad layer/vocab/position counts");
     ARB_REQUIRE(max_tokens > 0 && max_seq > 0 && max_seq <= 768, "mpnet_create: bad max_tokens=%lld / max_seq=%d",
@@ -340,15 +352,12 @@ int arb_mpnet_create(const ArbMpnetConfig* cfg, const ArbMpnetWeights* weights, 
     Mpnet* m = new (std::nothrow) Mpnet();
     ARB_REQUIRE(m != nullptr, "mpnet_create: out of host memory");
     m->cfg = *cfg;
-    m->fp16 = cfg->compute_dtype == ARB_DTYPE_F16;
-    // The cluster kernel that folds the post-LN into the residual GEMM (gemm16_ln_kernel) is correct
-    // but measured slower than GEMM + LayerNorm pass at the bench shape (1.21 vs 0.46+0.21 ms for
-    // K=768, 2.64 vs 1.43+0.21 ms for K=3072): its per-tile epilogue chain (residual TMA, DSMEM
-    // rendezvous of 3 CTAs, normalise, store) is ~3x the tile's MMA time and only two TMEM
-    // accumulators exist to hide it. It stays available through arb_gemm16_residual_ln; the
-    // encoder keeps the two-kernel path until the chain is shortened.
-    m->fuse_ln = false;
-    // What the encoder does instead: fold the LayerNorms into the neighbouring GEMM epilogues
+    if (int rc = dtype16(cfg->compute_dtype, &m->fmt)) {
+        delete m;
+        return rc;
+    }
+    m->short_f16 = cfg->compute_dtype == ARB_DTYPE_BF16_WF16;
+    // The LayerNorms are folded into the neighbouring GEMM epilogues
     // (EPI_LNIN_* / EPI_*_STATS, kernels.h). ARB_FOLD_LN=0 keeps the GEMM + LayerNorm-pass path
     // (the A/B baseline; both are parity-tested).
     const char* fold_env = getenv("ARB_FOLD_LN");
@@ -357,6 +366,17 @@ int arb_mpnet_create(const ArbMpnetConfig* cfg, const ArbMpnetWeights* weights, 
     m->max_tokens = max_tokens;
     m->max_seq = max_seq;
     int rc = mpnet_build(m, weights);
+    if (rc == ARB_OK) {
+        // status word the kernels write on a data error (out-of-range token id): pinned, host-mapped
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&m->status_host), 4 * sizeof(int), cudaHostAllocMapped);
+        if (e == cudaSuccess) e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&m->status_dev), m->status_host, 0);
+        if (e != cudaSuccess) {
+            set_error("mpnet_create: status word allocation failed: %s", cudaGetErrorString(e));
+            rc = ARB_ERR_CUDA;
+        } else {
+            memset(m->status_host, 0, 4 * sizeof(int));
+        }
+    }
     if (rc) {
         delete m;
         return rc;
@@ -377,7 +397,7 @@ int arb_mpnet_launches_per_encode(void* handle) {
     if (!handle) return 0;
     const Mpnet* m = static_cast<Mpnet*>(handle);
     if (m->fold_ln) return 3 + 5 * m->cfg.num_layers;  // embed, 5 per layer, final LayerNorm, pool
-    return 2 + (m->fuse_ln ? 5 : 7) * m->cfg.num_layers;
+    return 2 + 7 * m->cfg.num_layers;
 }
 
 int arb_mpnet_encode(void* handle, const int32_t* ids_dev, const int32_t* mask_dev, int32_t B,
@@ -388,7 +408,24 @@ int arb_mpnet_encode(void* handle, const int32_t* ids_dev, const int32_t* mask_d
     ARB_REQUIRE(S <= m->max_seq, "mpnet_encode: S=%d exceeds max_seq=%d", S, m->max_seq);
     ARB_REQUIRE(static_cast<int64_t>(B) * S <= m->max_tokens, "mpnet_encode: B*S=%lld exceeds max_tokens=%lld",
                 (long long)B * S, (long long)m->max_tokens);
+    int cur = -1;
+    ARB_CHECK_CUDA(cudaGetDevice(&cur));
+    ARB_REQUIRE(cur == m->device, "mpnet_encode: the handle lives on device %d but the current device is %d", m->device, cur);
     return mpnet_encode(m, ids_dev, mask_dev, B, S, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int arb_mpnet_short_seq(void* handle) {
+    return handle && static_cast<Mpnet*>(handle)->short_f16 ? kShortSeq : 0;
+}
+
+int arb_mpnet_status(void* handle) {
+    ARB_REQUIRE(handle != nullptr, "mpnet_status: null handle");
+    Mpnet* m = static_cast<Mpnet*>(handle);
+    volatile int* st = m->status_host;
+    if (st[0] == 0) return ARB_OK;
+    set_error("mpnet_encode: token id %d at token index %d is outside the vocabulary [0, %d)", st[1], st[2], m->cfg.vocab_size);
+    st[0] = 0;
+    return ARB_ERR_INVALID;
 }
 
 size_t arb_topk_search_workspace_bytes(int32_t dtype, int64_t Q, int64_t N, int32_t D, int32_t k) {
@@ -422,14 +459,14 @@ int arb_topk_merge(const float* scores_dev, const int64_t* ids_dev, int32_t G, i
                              static_cast<cudaStream_t>(stream));
 }
 
-static int dtype16(int32_t dtype, bool* fp16);
+
 
 int arb_gemm16_lnfold(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias,
                       const void* R, int64_t ldr, const float* colsum, const float* gamma, const float* beta,
                       const float* stats_in, int32_t parts_in, int32_t width_in, float* stats_out, float eps, int64_t M,
                       int32_t N, int32_t K, int32_t epilogue, int32_t dtype, void* stream) {
-    bool fp16;
-    if (int rc = dtype16(dtype, &fp16)) return rc;
+    int fmt;
+    if (int rc = dtype16(dtype, &fmt)) return rc;
     LnFoldArgs f;
     f.colsum = colsum;
     f.gamma = gamma;
@@ -440,7 +477,7 @@ int arb_gemm16_lnfold(const void* A, int64_t lda, const void* B, int64_t ldb, vo
     f.inv_width_in = width_in > 0 ? 1.0f / static_cast<float>(width_in) : 0.f;
     f.eps = eps;
     return launch_gemm16_fold(static_cast<const h16*>(A), lda, static_cast<const h16*>(B), ldb, static_cast<h16*>(C), ldc, bias,
-                              static_cast<const h16*>(R), ldr, M, N, K, epilogue, f, fp16, static_cast<cudaStream_t>(stream));
+                              static_cast<const h16*>(R), ldr, M, N, K, epilogue, f, fmt, static_cast<cudaStream_t>(stream));
 }
 
 size_t arb_topk_exchange_bytes(int32_t G, size_t slot_bytes) { return G > 0 ? topk_exchange_bytes(G, slot_bytes) : 0; }
@@ -511,50 +548,40 @@ int arb_topk_merge_records(const void* records_dev, int32_t G, int64_t Q, int32_
                                      static_cast<cudaStream_t>(stream));
 }
 
-static int dtype16(int32_t dtype, bool* fp16) {
-    ARB_REQUIRE(dtype == ARB_DTYPE_BF16 || dtype == ARB_DTYPE_F16, "dtype %d must be ARB_DTYPE_BF16 or ARB_DTYPE_F16", dtype);
-    *fp16 = dtype == ARB_DTYPE_F16;
-    return ARB_OK;
-}
 
 int arb_gemm16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                const float* bias, const void* R, int64_t ldr, int64_t M, int32_t N, int32_t K,
                int32_t epilogue, int32_t dtype, void* stream) {
-    bool f;
-    if (int rc = dtype16(dtype, &f)) return rc;
+    int fmt;
+    if (int rc = dtype16(dtype, &fmt)) return rc;
+    const bool f = fmt_act_f16(fmt);
+    (void)f;
     return launch_gemm16(static_cast<const h16*>(A), lda, static_cast<const h16*>(B), ldb, static_cast<h16*>(C),
-                         ldc, bias, static_cast<const h16*>(R), ldr, M, N, K, epilogue, f,
+                         ldc, bias, static_cast<const h16*>(R), ldr, M, N, K, epilogue, fmt,
                          static_cast<cudaStream_t>(stream));
-}
-
-int arb_gemm16_residual_ln(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
-                           const float* bias, const void* R, int64_t ldr, const float* gamma,
-                           const float* beta, float eps, int64_t M, int32_t N, int32_t K, int32_t dtype,
-                           void* stream) {
-    bool f;
-    if (int rc = dtype16(dtype, &f)) return rc;
-    return launch_gemm16_ln(static_cast<const h16*>(A), lda, static_cast<const h16*>(B), ldb, static_cast<h16*>(C),
-                            ldc, bias, static_cast<const h16*>(R), ldr, gamma, beta, eps, M, N, K, f,
-                            static_cast<cudaStream_t>(stream));
 }
 
 int arb_gemm16_f32out(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
                       int64_t M, int32_t N, int32_t K, int32_t dtype, void* stream) {
-    bool f;
-    if (int rc = dtype16(dtype, &f)) return rc;
+    int fmt;
+    if (int rc = dtype16(dtype, &fmt)) return rc;
+    const bool f = fmt_act_f16(fmt);
+    (void)f;
     return launch_gemm16_f32out(static_cast<const h16*>(A), lda, static_cast<const h16*>(B), ldb, C, ldc, M, N,
-                                K, f, static_cast<cudaStream_t>(stream));
+                                K, fmt, static_cast<cudaStream_t>(stream));
 }
 
 int arb_embed_layernorm(const int32_t* ids, const float* word_emb, const float* pos_emb,
                         const float* gamma, const float* beta, void* out16, int32_t B, int32_t S,
                         int32_t H, int32_t vocab, int32_t max_pos, int32_t pad_id, int32_t position_mode,
                         float eps, int32_t dtype, void* stream) {
-    bool f;
-    if (int rc = dtype16(dtype, &f)) return rc;
+    int fmt;
+    if (int rc = dtype16(dtype, &fmt)) return rc;
+    const bool f = fmt_act_f16(fmt);
+    (void)f;
     ARB_REQUIRE(position_mode == 0 || position_mode == 1, "embed_layernorm: position_mode %d must be 0 or 1", position_mode);
     return launch_embed_ln(ids, word_emb, pos_emb, gamma, beta, static_cast<h16*>(out16), B, S, H, vocab,
-                           max_pos, pad_id, position_mode, eps, f, static_cast<cudaStream_t>(stream));
+                           max_pos, pad_id, position_mode, eps, f, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int arb_adjacent_cosine(const float* emb_dev, int64_t n, int32_t D, float* out_dev, void* stream) {
@@ -563,8 +590,10 @@ int arb_adjacent_cosine(const float* emb_dev, int64_t n, int32_t D, float* out_d
 
 int arb_layernorm16(const void* x, const float* gamma, const float* beta, void* out, int64_t rows,
                     int32_t H, float eps, int32_t dtype, void* stream) {
-    bool f;
-    if (int rc = dtype16(dtype, &f)) return rc;
+    int fmt;
+    if (int rc = dtype16(dtype, &fmt)) return rc;
+    const bool f = fmt_act_f16(fmt);
+    (void)f;
     return launch_layernorm(static_cast<const h16*>(x), gamma, beta, static_cast<h16*>(out), rows, H, eps, f,
                             static_cast<cudaStream_t>(stream));
 }
@@ -572,16 +601,20 @@ int arb_layernorm16(const void* x, const float* gamma, const float* beta, void* 
 int arb_attention16(const void* qkv, const float* rel_bias, int32_t max_rel, const int32_t* mask,
                     void* ctx, int32_t B, int32_t S, int32_t heads, int32_t head_dim, int32_t dtype,
                     int32_t impl, void* stream) {
-    bool f;
-    if (int rc = dtype16(dtype, &f)) return rc;
+    int fmt;
+    if (int rc = dtype16(dtype, &fmt)) return rc;
+    const bool f = fmt_act_f16(fmt);
+    (void)f;
     return launch_attention(static_cast<const h16*>(qkv), rel_bias, max_rel, mask, static_cast<h16*>(ctx), B, S,
                             heads, head_dim, f, impl, static_cast<cudaStream_t>(stream));
 }
 
 int arb_pool_normalize(const void* hidden16, const int32_t* mask, float* out, int32_t B, int32_t S,
                        int32_t H, int32_t dtype, void* stream) {
-    bool f;
-    if (int rc = dtype16(dtype, &f)) return rc;
+    int fmt;
+    if (int rc = dtype16(dtype, &fmt)) return rc;
+    const bool f = fmt_act_f16(fmt);
+    (void)f;
     return launch_pool_normalize(static_cast<const h16*>(hidden16), mask, out, B, S, H, f,
                                  static_cast<cudaStream_t>(stream));
 }

@@ -102,13 +102,16 @@ __device__ __forceinline__ float gelu_tanh_fit(float x) {
     return fmaf(h, t, h);
 }
 
+// kF16 = format of the 16-bit ACTIVATIONS (A, C, R); the weights' format (B) only enters through
+// the instruction descriptor `idesc`, a kernel argument, so bf16 activations x fp16 weights is
+// the same kernel as the uniform-format cases.
 // OutT = h16 (16-bit activations in the kF16 format) or float. k2Cta: launched as clusters of two
 // CTAs that share one 256 x 256 tile through tcgen05 cta_group::2 (see umma_pipe.cuh).
 template <int EPI, bool kF16, typename OutT, bool k2Cta>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
-              const float* __restrict__ bias, int64_t M, int N, int K, const LnFoldArgs fold) {
+              const float* __restrict__ bias, int64_t M, int N, int K, const LnFoldArgs fold, const uint32_t idesc) {
     constexpr int BN = kGemmBN;
     constexpr int CW = 128 / static_cast<int>(sizeof(OutT));  // columns per staging chunk
     constexpr int CPG = (BN / 2) / CW;                        // chunks per group per tile
@@ -149,9 +152,9 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     } else if (warp == 1) {
         if (elect_one()) {
             if constexpr (k2Cta) {
-                if (rank == 0) pipe2_mma<SM, kF16>(sm, tmem_base, it, kblocks);
+                if (rank == 0) pipe2_mma<SM>(sm, tmem_base, it, kblocks, idesc);
             } else {
-                pipe_mma<SM, kF16>(sm, tmem_base, it, kblocks);
+                pipe_mma<SM>(sm, tmem_base, it, kblocks, idesc);
             }
         }
     } else {
@@ -387,7 +390,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 template <int EPI, bool kF16, typename OutT>
 static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb, OutT* C,
                             int64_t ldc, const float* bias, const h16* R, int64_t ldr, int64_t M,
-                            int N, int K, cudaStream_t stream, const LnFoldArgs& fold = LnFoldArgs()) {
+                            int N, int K, bool w_fp16, cudaStream_t stream, const LnFoldArgs& fold = LnFoldArgs()) {
     constexpr bool kRes = EPI == EPI_BIAS_RESIDUAL || EPI == EPI_BIAS_LNRES_STATS || EPI == EPI_BIAS_RES_STATS;
     CUtensorMap ta, tb, tc, tr;
     // the TMA element type only matters for OOB fill; both 16-bit formats move as raw 2-byte words
@@ -429,7 +432,7 @@ static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        ARB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tr, bias, M, N, K, fold));
+        ARB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tr, bias, M, N, K, fold, umma_idesc_16bit(2 * kBM, kGemmBN, kF16, w_fp16)));
         return ARB_OK;
     }
     auto kern = gemm16_kernel<EPI, kF16, OutT, false>;
@@ -438,246 +441,8 @@ static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb
     ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + kGemmBN - 1) / kGemmBN);
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, tc, tr, bias, M, N, K, fold);
+    kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, tc, tr, bias, M, N, K, fold, umma_idesc_16bit(kBM, kGemmBN, kF16, w_fp16));
     ARB_CHECK_CUDA(cudaGetLastError());
-    return ARB_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// C = LayerNorm(A . B^T + bias + R) * gamma + beta, fused: the post-LN of MPNetAttention
-// (modeling_mpnet.py:210) and MPNetOutput (:242) folded into the o-projection / FFN-down GEMM.
-// A row of N = CL*256 columns is spread over the CL CTAs of a thread-block cluster (one 128x256
-// tile each). Every epilogue thread keeps its 128 pre-LN values (rounded to 16 bit, the same
-// rounding point as the unfused path) in registers, publishes (sum, sum of squares) of its part
-// of the row in shared memory, signals an mbarrier in every CTA of the cluster, and reads the CL*2
-// partials of its row back through distributed shared memory — the pre-LN tensor never exists
-// in HBM and no separate LayerNorm pass runs.
-constexpr int kLnStages = 3;  // 3 x 48 KB ring leaves room for the staging tiles and the partials
-using LnSmem = PipeSmem<kGemmBN, kLnStages, 2 * kStageTileBytes>;
-
-struct LnTileIter {
-    int mblk, step, num_m, row_b;
-    __device__ __forceinline__ bool next(int& row_a, int& rb) {
-        if (mblk >= num_m) return false;
-        row_a = mblk * kBM;
-        rb = row_b;
-        mblk += step;
-        return true;
-    }
-};
-
-template <bool kF16>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm16_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
-                 const float* __restrict__ bias, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, float eps, int64_t M, int N, int K) {
-    constexpr int BN = kGemmBN;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    LnSmem sm{smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)};
-    const int warp = __shfl_sync(0xffffffff, threadIdx.x / 32, 0);
-    const int lane = threadIdx.x & 31;
-    const int CL = static_cast<int>(cluster_nctarank());
-    const int rank = static_cast<int>(cluster_ctarank());
-    const int num_m = static_cast<int>((M + kBM - 1) / kBM);
-    const int kblocks = (K + kBK - 1) / kBK;
-    LnTileIter it{static_cast<int>(blockIdx.x) / CL, static_cast<int>(gridDim.x) / CL, num_m, rank * BN};
-
-    float2* part = reinterpret_cast<float2*>(sm.extra());                  // [parity][group][row]
-    uint64_t* ln_bar = reinterpret_cast<uint64_t*>(sm.extra() + 2 * 2 * kBM * 8);  // [parity]
-    if (warp == 0 && elect_one()) {
-        mbar_init(ln_bar + 0, CL * 2);
-        mbar_init(ln_bar + 1, CL * 2);
-    }
-    const uint32_t tmem_base = pipe_setup(sm, warp, &tmap_a, &tmap_b, kEpiThreads);
-    cluster_sync_all();  // every CTA's barriers exist before any remote arrive
-
-    if (warp == 0) {
-        if (elect_one()) pipe_produce(sm, &tmap_a, &tmap_b, it, kblocks, kEvictNormal, kEvictLast);
-    } else if (warp == 1) {
-        if (elect_one()) pipe_mma<LnSmem, kF16>(sm, tmem_base, it, kblocks);
-    } else {
-        const int ew = warp - 2;
-        const int grp = ew >> 2;
-        const int lane_grp = warp & 3;
-        const int trow = lane_grp * 32 + lane;
-        const bool leader = (ew & 3) == 0 && lane == 0;
-        uint8_t* stage_tile = sm.pre() + grp * kStageTileBytes;
-        uint8_t* my_row = stage_tile + trow * 128;
-        const int sw = trow & 7;
-        uint64_t* res_bar = sm.aux(grp);
-        uint32_t res_phase = 0;
-        if (leader) {
-            tma_prefetch_desc(&tmap_c);
-            tma_prefetch_desc(&tmap_r);
-        }
-        const float inv_n = 1.0f / static_cast<float>(N);
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        int lt = 0;
-        int row_a, row_b;
-        while (it.next(row_a, row_b)) {
-            const int par = lt & 1;
-            mbar_wait(sm.tmem_full(acc), acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
-                                   static_cast<uint32_t>(acc * BN + grp * (BN / 2));
-            uint32_t keep[2][32];  // this thread's 128 pre-LN values, packed 16-bit
-            float sum = 0.f, sq = 0.f;
-            // ---- phase A: v = acc + bias + residual; row statistics; keep v
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int col0 = row_b + grp * (BN / 2) + c * 64;
-                if (leader) {
-                    tma_store_wait_read<0>();
-                    mbar_arrive_expect_tx(res_bar, kStageTileBytes);
-                    tma_load_2d(&tmap_r, res_bar, stage_tile, col0, row_a, kEvictFirst);
-                }
-                uint32_t r[64];
-                tmem_ld_32x32(taddr + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-                tmem_ld_32x32(taddr + c * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-                tmem_ld_wait();
-                if (c == 1) {
-                    tc_fence_before();
-                    mbar_arrive(sm.tmem_empty(acc));
-                }
-                float v[64];
-                const float4* bp = reinterpret_cast<const float4*>(bias + col0);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float4 b4 = __ldg(bp + j);
-                    v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4.x;
-                    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
-                    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
-                    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
-                }
-                mbar_wait(res_bar, res_phase);
-                res_phase ^= 1;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint4 u = *reinterpret_cast<const uint4*>(my_row + ((j ^ sw) << 4));
-                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float2 f = unpack16x2<kF16>(w[q]);
-                        v[8 * j + 2 * q] += f.x;
-                        v[8 * j + 2 * q + 1] += f.y;
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 64; j += 2) {
-                    sum += v[j] + v[j + 1];
-                    sq = fmaf(v[j], v[j], sq);
-                    sq = fmaf(v[j + 1], v[j + 1], sq);
-                    keep[c][j >> 1] = pack16x2<kF16>(v[j], v[j + 1]);
-                }
-            }
-            // ---- exchange the row statistics across the cluster through distributed shared memory
-            part[(par * 2 + grp) * kBM + trow] = make_float2(sum, sq);
-            named_bar_sync(1 + grp, 128);  // this group's 128 partials are written
-            if (leader) {
-                const uint32_t bar_local = smem_u32(ln_bar + par);
-                for (int rr = 0; rr < CL; ++rr) mbar_arrive_remote(map_to_cta(bar_local, rr));
-            }
-            // CTA-scope wait on purpose: a cluster-scope acquire makes ptxas emit CCTL.IVALL (a full
-            // L1D invalidate per thread per tile). The partials are read with ld.shared::cluster,
-            // which never goes through L1, and the writers' release.cluster arrive orders their
-            // st.shared before the arrival that completes this phase.
-            mbar_wait(ln_bar + par, (lt >> 1) & 1);
-            float tsum = 0.f, tsq = 0.f;
-            for (int rr = 0; rr < CL; ++rr) {
-#pragma unroll
-                for (int g2 = 0; g2 < 2; ++g2) {
-                    const float2 p = ld_dsmem_f32x2(map_to_cta(smem_u32(part + (par * 2 + g2) * kBM + trow), rr));
-                    tsum += p.x;
-                    tsq += p.y;
-                }
-            }
-            const float mean = tsum * inv_n;
-            const float rstd = rsqrtf(fmaxf(tsq * inv_n - mean * mean, 0.f) + eps);
-            // ---- phase B: normalise the kept values, stage, TMA store
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int col0 = row_b + grp * (BN / 2) + c * 64;
-                if (leader) tma_store_wait_read<0>();
-                named_bar_sync(1 + grp, 128);  // staging tile is free (residual consumed / store drained)
-                const float4* gp = reinterpret_cast<const float4*>(gamma + col0);
-                const float4* bp = reinterpret_cast<const float4*>(beta + col0);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 g0 = __ldg(gp + 2 * j), g1 = __ldg(gp + 2 * j + 1);
-                    const float4 b0 = __ldg(bp + 2 * j), b1 = __ldg(bp + 2 * j + 1);
-                    const float2 x0 = unpack16x2<kF16>(keep[c][4 * j + 0]);
-                    const float2 x1 = unpack16x2<kF16>(keep[c][4 * j + 1]);
-                    const float2 x2 = unpack16x2<kF16>(keep[c][4 * j + 2]);
-                    const float2 x3 = unpack16x2<kF16>(keep[c][4 * j + 3]);
-                    uint4 u;
-                    u.x = pack16x2<kF16>((x0.x - mean) * rstd * g0.x + b0.x, (x0.y - mean) * rstd * g0.y + b0.y);
-                    u.y = pack16x2<kF16>((x1.x - mean) * rstd * g0.z + b0.z, (x1.y - mean) * rstd * g0.w + b0.w);
-                    u.z = pack16x2<kF16>((x2.x - mean) * rstd * g1.x + b1.x, (x2.y - mean) * rstd * g1.y + b1.y);
-                    u.w = pack16x2<kF16>((x3.x - mean) * rstd * g1.z + b1.z, (x3.y - mean) * rstd * g1.w + b1.w);
-                    *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = u;
-                }
-                fence_proxy_async_smem();
-                named_bar_sync(1 + grp, 128);
-                if (leader) {
-                    tma_store_2d(&tmap_c, stage_tile, col0, row_a);
-                    tma_store_commit();
-                }
-            }
-            ++lt;
-            if (++acc == 2) {
-                acc = 0;
-                acc_phase ^= 1;
-            }
-        }
-        if (leader) tma_store_wait<0>();
-    }
-    pipe_teardown(sm, warp, tmem_base);
-    cluster_sync_all();  // no CTA may exit while a peer can still read its partials
-}
-
-bool gemm16_ln_supported(int N) { return N % kGemmBN == 0 && N / kGemmBN >= 1 && N / kGemmBN <= 8; }
-
-template <bool kF16>
-static int launch_gemm_ln_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
-                               const float* bias, const h16* R, int64_t ldr, const float* gamma,
-                               const float* beta, float eps, int64_t M, int N, int K, cudaStream_t stream) {
-    CUtensorMap ta, tb, tc, tr;
-    const bool ok = make_tmap_bf16_k64(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), kBM) &&
-                    make_tmap_bf16_k64(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), kGemmBN) &&
-                    make_tmap_rows128(&tc, C, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldc), 2) &&
-                    make_tmap_rows128(&tr, R, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldr), 2);
-    if (!ok) {
-        set_error("gemm_ln: cuTensorMapEncodeTiled failed");
-        return ARB_ERR_CUDA;
-    }
-    auto kern = gemm16_ln_kernel<kF16>;
-    constexpr int smem = LnSmem::kExtraOffset + 2 * 2 * kBM * 8 + 16 + 1024;
-    static_assert(smem <= 232448, "LN GEMM shared memory exceeds 227 KB");
-    ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int CL = N / kGemmBN;
-    if (CL > 8) {
-        set_error("gemm_ln: N=%d needs a cluster of %d CTAs (max 8)", N, CL);
-        return ARB_ERR_UNSUPPORTED;
-    }
-    const int64_t num_m = (M + kBM - 1) / kBM;
-    int64_t nclusters = num_sms() / CL;
-    if (nclusters > num_m) nclusters = num_m;
-    if (nclusters < 1) nclusters = 1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(nclusters * CL));
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = static_cast<unsigned>(CL);
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    ARB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tr, bias, gamma, beta, eps, M, N, K));
     return ARB_OK;
 }
 
@@ -698,16 +463,16 @@ static int check_gemm_args(const void* A, int64_t lda, const void* B, int64_t ld
 template <bool kF16>
 static int dispatch_gemm16(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
                            const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
-                           int epilogue, cudaStream_t stream) {
+                           int epilogue, bool w_fp16, cudaStream_t stream) {
     switch (epilogue) {
         case EPI_BIAS:
-            return launch_gemm_impl<EPI_BIAS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, stream);
+            return launch_gemm_impl<EPI_BIAS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, w_fp16, stream);
         case EPI_BIAS_GELU:
-            return launch_gemm_impl<EPI_BIAS_GELU, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, stream);
+            return launch_gemm_impl<EPI_BIAS_GELU, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, w_fp16, stream);
         case EPI_BIAS_RESIDUAL:
             ARB_REQUIRE(R != nullptr && ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0,
                         "gemm: residual operand missing or misaligned");
-            return launch_gemm_impl<EPI_BIAS_RESIDUAL, kF16, h16>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, stream);
+            return launch_gemm_impl<EPI_BIAS_RESIDUAL, kF16, h16>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, w_fp16, stream);
         default:
             set_error("gemm: unknown epilogue %d", epilogue);
             return ARB_ERR_INVALID;
@@ -716,34 +481,35 @@ static int dispatch_gemm16(const h16* A, int64_t lda, const h16* B, int64_t ldb,
 
 int launch_gemm16(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
                   const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
-                  int epilogue, bool fp16, cudaStream_t stream) {
+                  int epilogue, int fmt, cudaStream_t stream) {
     int rc = check_gemm_args(A, lda, B, ldb, C, ldc, M, N, K, 2);
     if (rc) return rc;
     ARB_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
                 "gemm: bias must be 16-byte aligned");
-    return fp16 ? dispatch_gemm16<true>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, stream)
-                : dispatch_gemm16<false>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, stream);
+    const bool w16 = fmt_w_f16(fmt);
+    return fmt_act_f16(fmt) ? dispatch_gemm16<true>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, w16, stream)
+                            : dispatch_gemm16<false>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, w16, stream);
 }
 
 template <bool kF16>
 static int dispatch_gemm16_fold(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
                                 const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
-                                int epilogue, const LnFoldArgs& f, cudaStream_t stream) {
+                                int epilogue, const LnFoldArgs& f, bool w_fp16, cudaStream_t stream) {
     switch (epilogue) {
         case EPI_LNIN_BIAS:
-            return launch_gemm_impl<EPI_LNIN_BIAS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, stream, f);
+            return launch_gemm_impl<EPI_LNIN_BIAS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, w_fp16, stream, f);
         case EPI_LNIN_BIAS_GELU:
-            return launch_gemm_impl<EPI_LNIN_BIAS_GELU, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, stream, f);
+            return launch_gemm_impl<EPI_LNIN_BIAS_GELU, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, w_fp16, stream, f);
         case EPI_BIAS_LNRES_STATS:
-            return launch_gemm_impl<EPI_BIAS_LNRES_STATS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, stream, f);
+            return launch_gemm_impl<EPI_BIAS_LNRES_STATS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, w_fp16, stream, f);
         default:
-            return launch_gemm_impl<EPI_BIAS_RES_STATS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, stream, f);
+            return launch_gemm_impl<EPI_BIAS_RES_STATS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, w_fp16, stream, f);
     }
 }
 
 int launch_gemm16_fold(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
                        const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
-                       int epilogue, const LnFoldArgs& f, bool fp16, cudaStream_t stream) {
+                       int epilogue, const LnFoldArgs& f, int fmt, cudaStream_t stream) {
     int rc = check_gemm_args(A, lda, B, ldb, C, ldc, M, N, K, 2);
     if (rc) return rc;
     ARB_REQUIRE(epilogue >= EPI_LNIN_BIAS && epilogue <= EPI_BIAS_RES_STATS, "gemm_fold: unknown epilogue %d", epilogue);
@@ -765,31 +531,18 @@ int launch_gemm16_fold(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16
     if (epilogue == EPI_BIAS_LNRES_STATS)
         ARB_REQUIRE(f.gamma && f.beta && (reinterpret_cast<uintptr_t>(f.gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(f.beta) & 15) == 0,
                     "gemm_fold: gamma / beta missing or misaligned");
-    return fp16 ? dispatch_gemm16_fold<true>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, f, stream)
-                : dispatch_gemm16_fold<false>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, f, stream);
-}
-
-int launch_gemm16_ln(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
-                     const float* bias, const h16* R, int64_t ldr, const float* gamma, const float* beta,
-                     float eps, int64_t M, int N, int K, bool fp16, cudaStream_t stream) {
-    int rc = check_gemm_args(A, lda, B, ldb, C, ldc, M, N, K, 2);
-    if (rc) return rc;
-    ARB_REQUIRE(gemm16_ln_supported(N), "gemm_ln: N=%d must be a multiple of 256, at most 2048", N);
-    ARB_REQUIRE(bias && gamma && beta && R, "gemm_ln: bias, gamma, beta and the residual are required");
-    ARB_REQUIRE(ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(beta) & 15) == 0,
-                "gemm_ln: residual / bias / gamma / beta must be 16-byte aligned");
-    return fp16 ? launch_gemm_ln_impl<true>(A, lda, B, ldb, C, ldc, bias, R, ldr, gamma, beta, eps, M, N, K, stream)
-                : launch_gemm_ln_impl<false>(A, lda, B, ldb, C, ldc, bias, R, ldr, gamma, beta, eps, M, N, K, stream);
+    const bool w16 = fmt_w_f16(fmt);
+    return fmt_act_f16(fmt) ? dispatch_gemm16_fold<true>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, f, w16, stream)
+                            : dispatch_gemm16_fold<false>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, f, w16, stream);
 }
 
 int launch_gemm16_f32out(const h16* A, int64_t lda, const h16* B, int64_t ldb, float* C,
-                         int64_t ldc, int64_t M, int N, int K, bool fp16, cudaStream_t stream) {
+                         int64_t ldc, int64_t M, int N, int K, int fmt, cudaStream_t stream) {
     int rc = check_gemm_args(A, lda, B, ldb, C, ldc, M, N, K, 4);
     if (rc) return rc;
-    return fp16 ? launch_gemm_impl<EPI_BIAS, true, float>(A, lda, B, ldb, C, ldc, nullptr, nullptr, 0, M, N, K, stream)
-                : launch_gemm_impl<EPI_BIAS, false, float>(A, lda, B, ldb, C, ldc, nullptr, nullptr, 0, M, N, K, stream);
+    const bool w16 = fmt_w_f16(fmt);
+    return fmt_act_f16(fmt) ? launch_gemm_impl<EPI_BIAS, true, float>(A, lda, B, ldb, C, ldc, nullptr, nullptr, 0, M, N, K, w16, stream)
+                            : launch_gemm_impl<EPI_BIAS, false, float>(A, lda, B, ldb, C, ldc, nullptr, nullptr, 0, M, N, K, w16, stream);
 }
 
 }  // namespace arb

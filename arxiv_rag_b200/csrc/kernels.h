@@ -6,8 +6,18 @@
 
 namespace arb {
 
-// Encoder activations/weights are 16-bit in HBM: bf16 or fp16, chosen per handle (`fp16` flag).
+// Encoder activations/weights are 16-bit in HBM: bf16 or fp16.
 typedef uint16_t h16;
+
+// Operand formats of one launch (`fmt` arguments): the activations (A, C, R, q/k/v, ctx) and the
+// weights (the GEMM B operand) choose their 16-bit format independently — tcgen05 kind::f16 takes
+// the A and B formats as separate instruction-descriptor fields. The encoder's default mode is
+// bf16 activations x fp16 weights (FMT_W_F16): the weights' rounding error is systematic across
+// tokens and does not average out in the mean pool, so they get the 11-bit mantissa; the
+// activations keep the fp32 exponent range.
+enum : int { FMT_ACT_F16 = 1, FMT_W_F16 = 2 };
+inline bool fmt_act_f16(int fmt) { return (fmt & FMT_ACT_F16) != 0; }
+inline bool fmt_w_f16(int fmt) { return (fmt & FMT_W_F16) != 0; }
 
 enum GemmEpilogue : int {
     EPI_BIAS = 0,           // C = A.B^T + bias
@@ -39,25 +49,20 @@ struct LnFoldArgs {
 // C[M,N] = epi(A[M,K] . B[N,K]^T); A, B, C, R 16-bit row-major; bias fp32 [N] (may be null).
 int launch_gemm16(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
                   const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
-                  int epilogue, bool fp16, cudaStream_t stream);
+                  int epilogue, int fmt, cudaStream_t stream);
 // The folded-LayerNorm epilogues (3..6); N % 128 == 0 for the *_STATS ones.
 int launch_gemm16_fold(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
                        const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
-                       int epilogue, const LnFoldArgs& fold, bool fp16, cudaStream_t stream);
-// C = LayerNorm(A.B^T + bias + R) * gamma + beta in one kernel (cluster of N/256 CTAs per row block,
-// row statistics exchanged through distributed shared memory). N % 256 == 0, N <= 2048.
-bool gemm16_ln_supported(int N);
-int launch_gemm16_ln(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
-                     const float* bias, const h16* R, int64_t ldr, const float* gamma, const float* beta,
-                     float eps, int64_t M, int N, int K, bool fp16, cudaStream_t stream);
+                       int epilogue, const LnFoldArgs& fold, int fmt, cudaStream_t stream);
 // Same main loop, fp32 output, no epilogue math (used by the kernel parity tests).
 int launch_gemm16_f32out(const h16* A, int64_t lda, const h16* B, int64_t ldb, float* C,
-                         int64_t ldc, int64_t M, int N, int K, bool fp16, cudaStream_t stream);
+                         int64_t ldc, int64_t M, int N, int K, int fmt, cudaStream_t stream);
 
 // word_emb[ids] + pos_emb[position_ids(ids)] -> LayerNorm -> 16-bit hidden [B*S, H]
 int launch_embed_ln(const int32_t* ids, const float* word_emb, const float* pos_emb,
                     const float* gamma, const float* beta, h16* out, int B, int S, int H, int vocab,
                     int max_pos, int pad_id, int pos_mode /* 0 MPNet pad-aware, 1 absolute */, float eps, bool fp16,
+                    int* err_flag_dev /* nullable: [0]=1, [1]=id, [2]=token index on an out-of-range id */,
                     cudaStream_t stream);
 // out = LayerNorm(x) row-wise, x 16-bit [rows, H] (already holds GEMM output + residual).
 int launch_layernorm(const h16* x, const float* gamma, const float* beta, h16* out, int64_t rows,

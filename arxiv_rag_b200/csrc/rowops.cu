@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256)
 embed_ln_kernel(const int32_t* __restrict__ ids, const float* __restrict__ word_emb,
                 const float* __restrict__ pos_emb, const float* __restrict__ gamma,
                 const float* __restrict__ beta, h16* __restrict__ out, int S, int H,
-                int vocab, int max_pos, int pad_id, int pos_mode, float eps) {
+                int vocab, int max_pos, int pad_id, int pos_mode, float eps, int* __restrict__ err_flag) {
     extern __shared__ int smem_i[];
     int* s_pos = smem_i;              // [S] position id of each token
     int* s_chunk = smem_i + S;        // [ceil(S/32)] non-pad count per 32-token chunk
@@ -90,7 +90,18 @@ embed_ln_kernel(const int32_t* __restrict__ ids, const float* __restrict__ word_
     const int nvec = H / 128;
     for (int s = warp; s < S; s += nwarps) {
         int id = row_ids[s];
-        id = min(max(id, 0), vocab - 1);
+        if (id < 0 || id >= vocab) {
+            // torch's embedding raises on such an id. Report it through the handle's status word
+            // (host-mapped, read by arb_mpnet_status after the stream is synchronised) and clamp so
+            // the gather itself stays in bounds.
+            if (lane == 0 && err_flag != nullptr) {
+                err_flag[1] = id;
+                err_flag[2] = b * S + s;
+                __threadfence_system();
+                err_flag[0] = 1;
+            }
+            id = min(max(id, 0), vocab - 1);
+        }
         const float* w = word_emb + static_cast<int64_t>(id) * H;
         const float* p = pos_emb + static_cast<int64_t>(s_pos[s]) * H;
         float4 x[kMaxVec];
@@ -238,14 +249,15 @@ static int check_h(int H) {
 
 int launch_embed_ln(const int32_t* ids, const float* word_emb, const float* pos_emb,
                     const float* gamma, const float* beta, h16* out, int B, int S, int H, int vocab,
-                    int max_pos, int pad_id, int pos_mode, float eps, bool fp16, cudaStream_t stream) {
+                    int max_pos, int pad_id, int pos_mode, float eps, bool fp16, int* err_flag_dev,
+                    cudaStream_t stream) {
     ARB_REQUIRE(ids && word_emb && pos_emb && gamma && beta && out, "embed_ln: null pointer");
     ARB_REQUIRE(B > 0 && S > 0 && S <= 4096, "embed_ln: bad shape B=%d S=%d", B, S);
     if (int rc = check_h(H)) return rc;
     const size_t smem = (S + (S + 31) / 32) * sizeof(int);
     auto kern = fp16 ? embed_ln_kernel<true> : embed_ln_kernel<false>;
     kern<<<B, 256, smem, stream>>>(ids, word_emb, pos_emb, gamma, beta, out, S, H, vocab, max_pos,
-                                   pad_id, pos_mode, eps);
+                                   pad_id, pos_mode, eps, err_flag_dev);
     ARB_CHECK_CUDA(cudaGetLastError());
     return ARB_OK;
 }

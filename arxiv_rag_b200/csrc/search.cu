@@ -208,9 +208,9 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     } else if (warp == 1) {
         if (elect_one()) {
             if constexpr (kPair) {
-                if (rank == 0) pipe2_mma<SM, false>(sm, tmem_base, it, kblocks);
+                if (rank == 0) pipe2_mma<SM>(sm, tmem_base, it, kblocks, umma_idesc_16bit(2 * kBM, SM::kBN, false));
             } else {
-                pipe_mma<SM, false>(sm, tmem_base, it, kblocks);
+                pipe_mma<SM>(sm, tmem_base, it, kblocks, umma_idesc_16bit(kBM, SM::kBN, false));
             }
         }
     } else {

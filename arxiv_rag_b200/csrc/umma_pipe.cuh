@@ -116,9 +116,10 @@ __device__ __forceinline__ void pipe_produce(const SM& sm, const void* tmap_a, c
 
 // MMA issuer: 4 x (128 x BN x 16) tcgen05.mma per K-block, accumulating in the TMEM buffer
 // that the epilogue has released; commits release the smem stage and publish the accumulator.
-template <class SM, bool kF16, class TileIter>
-__device__ __forceinline__ void pipe_mma(const SM& sm, uint32_t tmem_base, TileIter it, int kblocks) {
-    constexpr uint32_t idesc = umma_idesc_16bit(kBM, SM::kBN, kF16);
+// idesc: umma_idesc_16bit(kBM, SM::kBN, A format, B format) — a runtime value, so one kernel serves
+// every operand-format pair.
+template <class SM, class TileIter>
+__device__ __forceinline__ void pipe_mma(const SM& sm, uint32_t tmem_base, TileIter it, int kblocks, uint32_t idesc) {
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -221,9 +222,8 @@ __device__ __forceinline__ void pipe2_produce(const SM& sm, const void* tmap_a, 
 }
 
 // MMA issuer (leader CTA only): 4 x (256 x BN x 16) per K-block.
-template <class SM, bool kF16, class TileIter>
-__device__ __forceinline__ void pipe2_mma(const SM& sm, uint32_t tmem_base, TileIter it, int kblocks) {
-    constexpr uint32_t idesc = umma_idesc_16bit(2 * kBM, SM::kBN, kF16);
+template <class SM, class TileIter>
+__device__ __forceinline__ void pipe2_mma(const SM& sm, uint32_t tmem_base, TileIter it, int kblocks, uint32_t idesc) {
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;

@@ -42,11 +42,16 @@ class B200SentenceEncoder:
         max_length=..., return_tensors='np') -> {'input_ids', 'attention_mask'}` (a HF tokenizer).
         Without one, `encode` accepts pre-tokenised `(input_ids, attention_mask)`.
     max_batch / max_seq : capacity of the activation workspace (tokens = max_batch * max_seq).
-    dtype : 'bf16' (the BASELINE config) or 'fp16' — the 16-bit format of weights/activations and
-        tensor-core operands (fp32 accumulation and statistics either way). fp16's 3 extra
-        mantissa bits give cosine ~0.999998 vs fp32 on every row; bf16 gives ~0.99995 on full
-        rows but drops below 0.9999 on very short rows (DESIGN.md 'Numerics').
+    dtype : 16-bit formats of the tensor-core operands (fp32 accumulation and statistics always):
+        'bf16' (default, the BASELINE config) — bf16 activations x fp16 weights in one tcgen05.mma;
+        rows shorter than `short_seq` (32) tokens are batched apart and run with fp16 activations,
+        because a row of a few tokens has no averaging over its activation noise. Cosine vs the
+        fp32 reference >= 0.9999 on every row (DESIGN.md 'Numerics').
+        'fp16' — fp16 activations and weights (cosine ~0.999998 everywhere).
+        'bf16_pure' — bf16 activations and weights: the A/B baseline (~0.9998 on 1-token rows).
     """
+
+    DTYPES = {"bf16": _lib.ARB_DTYPE_BF16_WF16, "fp16": _lib.ARB_DTYPE_F16, "bf16_pure": _lib.ARB_DTYPE_BF16}
 
     def __init__(self, state_dict: dict | None = None, arch: MPNetArch = ALL_MPNET_BASE_V2,
                  device: int | None = None, max_batch: int = 1024, max_seq: int | None = None,
@@ -68,17 +73,20 @@ class B200SentenceEncoder:
         if state_dict is None:
             state_dict = synthetic_state_dict(arch, seed)
         packed = PackedWeights(arch, state_dict)
-        if dtype not in ("bf16", "fp16"):
-            raise ValueError("dtype must be 'bf16' (BASELINE config) or 'fp16'")
+        if dtype not in self.DTYPES:
+            raise ValueError(f"dtype must be one of {sorted(self.DTYPES)}")
         self.dtype = dtype
-        cfg = arch.c_struct(_lib.ARB_DTYPE_F16 if dtype == "fp16" else _lib.ARB_DTYPE_BF16)
+        cfg = arch.c_struct(self.DTYPES[dtype])
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().arb_mpnet_create(C.byref(cfg), C.byref(packed.struct),
                                                    self.max_batch * self.max_seq, self.max_seq,
                                                    self.device, C.byref(handle)))
         self._h = handle
-        self._staging = {}
+        # rows shorter than this are batched among themselves (the library runs such batches with
+        # fp16 activations); 0 = no split
+        self.short_seq = int(_lib.lib().arb_mpnet_short_seq(handle))
+        self._staging = None
 
     # ------------------------------------------------------------------ reference surface
     def get_sentence_embedding_dimension(self) -> int:
@@ -99,16 +107,32 @@ class B200SentenceEncoder:
             order = np.argsort(-lengths, kind="stable")  # longest first, like sentence-transformers
             bs = max(1, min(int(batch_size), self.max_batch))
             with torch.cuda.device(self.device):
-                for start in range(0, n, bs):
-                    sel = order[start:start + bs]
+                for sel in self._batches(order, lengths, bs):
                     S = max(int(lengths[sel].max()), 1)  # pad to the longest row of the batch
                     d_ids, d_mask = self._to_device(ids[sel, :S], mask[sel, :S])
                     emb = self.encode_tokens(d_ids, d_mask)
                     out[torch.from_numpy(sel).to(out.device)] = emb
         if convert_to_tensor:
+            self.check_status(synchronize=True)
             return out[0] if single else out
-        res = out.cpu().numpy()
+        res = out.cpu().numpy()  # synchronises the stream
+        self.check_status()
         return res[0] if single else res
+
+    def _batches(self, order: np.ndarray, lengths: np.ndarray, bs: int):
+        """Length-sorted rows cut into batches of `bs`; rows shorter than `short_seq` never share a
+        batch with longer ones (a batch's padded length decides its activation format)."""
+        n_long = int((lengths[order] >= self.short_seq).sum()) if self.short_seq else len(order)
+        for lo, hi in ((0, n_long), (n_long, len(order))):
+            for start in range(lo, hi, bs):
+                yield order[start:min(start + bs, hi)]
+
+    def check_status(self, synchronize: bool = False) -> None:
+        """Raise if a kernel of an earlier call met a token id outside the vocabulary (torch's
+        embedding raises there; the kernels clamp and flag). The stream must be idle."""
+        if synchronize:
+            self._torch.cuda.synchronize(self.device)
+        _lib.check(_lib.lib().arb_mpnet_status(self._h))
 
     # ------------------------------------------------------------------ device fast path
     def encode_tokens(self, ids_dev, mask_dev, out=None):
@@ -121,8 +145,10 @@ class B200SentenceEncoder:
         B, S = ids_dev.shape
         if out is None:
             out = torch.empty((B, self.arch.hidden_size), dtype=torch.float32, device=ids_dev.device)
-        _lib.check(_lib.lib().arb_mpnet_encode(self._h, _lib.ptr(ids_dev), _lib.ptr(mask_dev), B, S,
-                                               _lib.ptr(out), _lib.current_stream()))
+        # one handle = one device and one stream at a time (its activation buffers are shared)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().arb_mpnet_encode(self._h, _lib.ptr(ids_dev), _lib.ptr(mask_dev), B, S,
+                                                   _lib.ptr(out), _lib.current_stream()))
         return out
 
     def encode_tokens_graphed(self, ids_dev, mask_dev):
@@ -187,21 +213,23 @@ class B200SentenceEncoder:
         return ids.astype(np.int32, copy=False), mask.astype(np.int32, copy=False)
 
     def _to_device(self, ids: np.ndarray, mask: np.ndarray):
-        """Pinned staging + async H2D on the current stream."""
+        """Pinned staging + async H2D on the current stream. Two pinned buffers of the handle's
+        capacity, used alternately and sliced per batch: filling one overlaps the copy out of the
+        other, and no shape ever needs a new pinned allocation."""
         torch = self._torch
         B, S = ids.shape
-        key = (B, S)
-        if key not in self._staging:
-            if len(self._staging) > 64:
-                torch.cuda.synchronize(self.device)
-                self._staging.clear()
-            self._staging[key] = (torch.empty((2, B, S), dtype=torch.int32, pin_memory=True),
-                                  torch.cuda.Event())
-        st, ev = self._staging[key]
+        if self._staging is None:
+            cap = 2 * self.max_batch * self.max_seq
+            self._staging = [[torch.empty(cap, dtype=torch.int32, pin_memory=True), torch.cuda.Event()]
+                             for _ in range(2)]
+            self._staging_next = 0
+        st, ev = self._staging[self._staging_next]
+        self._staging_next ^= 1
         ev.synchronize()  # the previous H2D out of this pinned buffer must have drained
-        st[0].numpy()[...] = ids
-        st[1].numpy()[...] = mask
-        dev = st.to(f"cuda:{self.device}", non_blocking=True)
+        view = st[:2 * B * S].view(2, B, S)
+        view[0].numpy()[...] = ids
+        view[1].numpy()[...] = mask
+        dev = view.to(f"cuda:{self.device}", non_blocking=True)
         ev.record()
         return dev[0], dev[1]
 

@@ -139,6 +139,30 @@ class PackedWeights:
         self.struct.layers = C.cast(self.layers, C.POINTER(_lib.MpnetLayerWeights))
 
 
+def heavy_tail_state_dict(arch: MPNetArch = ALL_MPNET_BASE_V2, seed: int = 0) -> dict:
+    """`synthetic_state_dict` reshaped towards what trained encoders look like where it hurts
+    16-bit arithmetic: two outlier hidden channels (x20 rows of every FFN down-projection, the
+    "massive activation" channels of BERT-family models), LayerNorm gains up to 5 on a few
+    channels, and a relative-position table spread over +-8 (23 log2 units between the most and
+    the least favoured offset, which exercises the softmax shift). No checkpoint exists offline;
+    this is the stand-in the parity tests run both 16-bit modes on."""
+    sd = {k: np.array(v, copy=True) for k, v in synthetic_state_dict(arch, seed).items()}
+    rng = np.random.default_rng(seed + 7919)
+    H = arch.hidden_size
+    outliers = rng.choice(H, 2, replace=False)
+    key = "encoder.relative_attention_bias.weight"
+    if key in sd:
+        sd[key] = rng.uniform(-8.0, 8.0, sd[key].shape).astype(np.float32)
+    bert = arch.kind == "bert"
+    for l in range(arch.num_layers):
+        p = f"encoder.layer.{l}."
+        for nm in ("attention.output.LayerNorm" if bert else "attention.LayerNorm", "output.LayerNorm"):
+            sd[p + nm + ".weight"][rng.choice(H, 8, replace=False)] = rng.uniform(2.0, 5.0, 8).astype(np.float32)
+        sd[p + "output.dense.weight"][outliers, :] *= 20.0
+        sd[p + "output.dense.bias"][outliers] *= 20.0
+    return sd
+
+
 def synthetic_state_dict(arch: MPNetArch = ALL_MPNET_BASE_V2, seed: int = 0) -> dict:
     """Seeded random weights with the statistics of a trained encoder's parameter classes:
     N(0, 0.02) matrices/embeddings (HF init), and NON-trivial biases, LayerNorm gamma/beta and

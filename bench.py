@@ -230,7 +230,7 @@ def run_b200(args):
     ln_g, ln_b = torch.ones(768, device=dev), torch.zeros(768, device=dev)
     for (N, K, epi) in GEMM_SHAPES:
         A = A768 if K == 768 else A3072
-        W = (torch.randn(N, K, device=dev) * 0.04).to(torch.bfloat16)
+        W = (torch.randn(N, K, device=dev) * 0.04).to(torch.float16)  # the encode path's operands: bf16 activations x fp16 weights
         bias = torch.randn(N, device=dev)
         colsum = torch.randn(N, device=dev)
         fold_epi = {0: 3, 1: 4, 2: 5}[epi]  # bias -> LN-in bias; gelu -> LN-in gelu; residual -> LN(residual) + row stats
@@ -238,7 +238,7 @@ def run_b200(args):
                                                         Rbuf.data_ptr() if epi == 2 else 0, 768, colsum.data_ptr(), ln_g.data_ptr(),
                                                         ln_b.data_ptr(), stats_in.data_ptr(), parts, 768,
                                                         stats_out.data_ptr() if epi == 2 else 0, 1e-5, M, N, K, fold_epi,
-                                                        _lib.ARB_DTYPE_BF16, torch.cuda.current_stream().cuda_stream))
+                                                        _lib.ARB_DTYPE_BF16_WF16, torch.cuda.current_stream().cuda_stream))
         for _ in range(3):
             call()
         torch.cuda.synchronize()

@@ -40,6 +40,7 @@ extern "C" {
 #define ARB_DTYPE_F32 0
 #define ARB_DTYPE_BF16 1
 #define ARB_DTYPE_F16 2
+#define ARB_DTYPE_BF16_WF16 3 /* bf16 activations x fp16 weights (mixed tcgen05 operand formats) */
 
 #define ARB_EPI_BIAS 0
 #define ARB_EPI_BIAS_GELU 1
@@ -65,10 +66,20 @@ typedef struct ArbMpnetConfig {
     int32_t relative_attention_num_buckets; /* 32 */
     int32_t pad_token_id;                   /* 1 (MPNetEmbeddings.padding_idx, modeling_mpnet.py:60) */
     float layer_norm_eps;                   /* 1e-5 for all-mpnet-base-v2 */
-    int32_t compute_dtype;                  /* ARB_DTYPE_BF16 (BASELINE config) or ARB_DTYPE_F16:
-                                               16-bit format of weights + activations in HBM and
-                                               of the tensor-core operands; accumulation, softmax
-                                               and LayerNorm statistics are always fp32 */
+    int32_t compute_dtype;                  /* 16-bit formats in HBM and of the tensor-core operands
+                                               (accumulation, softmax and LayerNorm statistics are
+                                               always fp32):
+                                               ARB_DTYPE_BF16_WF16  the BASELINE "bf16" config as
+                                                 shipped: bf16 activations x fp16 weights in one
+                                                 tcgen05.mma (the weights' rounding error is the
+                                                 part of the bf16 budget that does not average out
+                                                 over tokens); batches padded to fewer than
+                                                 arb_mpnet_short_seq() tokens run with fp16
+                                                 activations — a row of a few tokens cannot reach
+                                                 cosine 0.9999 vs fp32 with bf16 activations;
+                                               ARB_DTYPE_F16   fp16 activations and weights;
+                                               ARB_DTYPE_BF16  bf16 activations and weights (A/B
+                                                 baseline; ~0.9998 on 1-token rows) */
     int32_t position_mode;                  /* 0 = MPNet: padding-aware position ids (modeling_mpnet.py:889-897);
                                                1 = BERT: absolute index (all-MiniLM-L6-v2; token-type row 0 is
                                                folded into the position table by the caller). A BERT-style
@@ -103,6 +114,14 @@ int64_t arb_mpnet_device_bytes(void* handle);
  * out: dev fp32 [B,hidden] unit-norm rows in input order. Rows whose mask is all zero -> 0. */
 int arb_mpnet_encode(void* handle, const int32_t* ids_dev, const int32_t* mask_dev, int32_t B,
                      int32_t S, float* out_dev, void* stream);
+/* Data errors found by the kernels of earlier arb_mpnet_encode calls (a token id outside
+ * [0, vocab_size) — torch's embedding raises on it; the kernel clamps the gather and records the
+ * id). Call after the stream has been synchronised: ARB_OK, or ARB_ERR_INVALID (message in
+ * arb_last_error(); the status is cleared). */
+int arb_mpnet_status(void* handle);
+/* ARB_DTYPE_BF16_WF16 handles: batches with S below this run with fp16 activations; hosts that sort
+ * rows by length should cut their batches at this length. 0 for the other dtypes. */
+int arb_mpnet_short_seq(void* handle);
 /* Number of kernel launches one arb_mpnet_encode call enqueues (for launch accounting). */
 int arb_mpnet_launches_per_encode(void* handle);
 /* MPNetEncoder.relative_position_bucket (modeling_mpnet.py:343-360) for relative_position = j-i. */
@@ -161,7 +180,8 @@ int arb_topk_search_launches(int32_t dtype);
 /* ------------------------------------------------------------------------------------------
  * Kernel-level entry points (each is one launch); used by the parity tests and available to
  * callers that want to compose the encoder themselves. All pointers are device pointers;
- * `dtype` is the 16-bit activation format (ARB_DTYPE_BF16 or ARB_DTYPE_F16).
+ * `dtype` gives the 16-bit formats: ARB_DTYPE_BF16 / ARB_DTYPE_F16 (activations and weights alike)
+ * or ARB_DTYPE_BF16_WF16 (A, C, R bf16; the GEMM B operand fp16).
  * ------------------------------------------------------------------------------------------ */
 /* GEMM with a LayerNorm folded into its epilogue (how the encoder avoids separate LayerNorm passes).
  * epilogue 3: C = rstd (A.B'^T - mean colsum) + bias          A rows are PRE-LayerNorm; B' = B diag(gamma),
@@ -185,12 +205,6 @@ int arb_gemm16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, 
                int32_t epilogue, int32_t dtype, void* stream);
 int arb_gemm16_f32out(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
                       int64_t M, int32_t N, int32_t K, int32_t dtype, void* stream);
-/* C = LayerNorm(A . B^T + bias + R) * gamma + beta fused in one kernel (post-LN of
- * modeling_mpnet.py:210 / :242); N % 256 == 0 and N <= 2048 (a cluster of N/256 CTAs per row block). */
-int arb_gemm16_residual_ln(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
-                           const float* bias, const void* R, int64_t ldr, const float* gamma,
-                           const float* beta, float eps, int64_t M, int32_t N, int32_t K, int32_t dtype,
-                           void* stream);
 int arb_embed_layernorm(const int32_t* ids, const float* word_emb, const float* pos_emb,
                         const float* gamma, const float* beta, void* out16, int32_t B, int32_t S,
                         int32_t H, int32_t vocab, int32_t max_pos, int32_t pad_id, int32_t position_mode,

@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.arb_abi_version() == 1
+    assert lib.arb_abi_version() == 2
 
 
 def test_struct_layout_matches_header():

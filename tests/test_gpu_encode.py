@@ -2,25 +2,24 @@
 committed golden vectors and against the oracle (transformers.MPNetModel + pooling) on the same
 seeded inputs; the reference-shaped worker API; edge cases.
 
-Tolerance (north_star): embedding cosine >= 0.9999 versus the fp32 reference. It holds for
-dtype='fp16' on every row and for dtype='bf16' (the BASELINE config) on rows of >= 16 tokens;
-bf16's 8-bit mantissa leaves very short rows (no token averaging) at >= 0.9995 — the bf16
-rounding of the weights alone already costs 6e-5 there (DESIGN.md 'Numerics',
-tests/test_oracle_encode.py::test_bf16_rounding_budget_documented)."""
+Tolerance (north_star): embedding cosine >= 0.9999 versus the fp32 reference on EVERY non-empty
+row, for both shipped modes: dtype='bf16' (the BASELINE config: bf16 activations x fp16 weights,
+rows shorter than 32 tokens batched apart and run with fp16 activations) and dtype='fp16'.
+dtype='bf16_pure' (bf16 weights too, no short-row routing) is kept as the A/B baseline and is
+tested at the budget tools/rounding_budget.py predicts for it (DESIGN.md 'Numerics')."""
 import os
 
 import numpy as np
 import pytest
 
 from arxiv_rag_b200 import generation
-from arxiv_rag_b200.weights import ALL_MPNET_BASE_V2, MPNetArch, synthetic_state_dict
+from arxiv_rag_b200.weights import ALL_MPNET_BASE_V2, MPNetArch, heavy_tail_state_dict, synthetic_state_dict
 from oracle import encode_oracle as eo
 from tests.conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
 COS_TOL = 0.9999
-COS_TOL_BF16_SHORT = 0.9995
 
 
 def _encoder(arch, sd, dtype, **kw):
@@ -40,24 +39,23 @@ def _assert_parity(got, ref, mask, dtype):
     nonempty = lens > 0
     assert np.allclose(np.linalg.norm(got[nonempty], axis=1), 1.0, atol=1e-5)
     assert (got[~nonempty] == 0).all()  # all-pad rows -> zero vector, as the oracle
-    if dtype == "fp16":
-        assert cos[nonempty].min() >= COS_TOL, cos
-    else:
-        long_rows = lens >= 16
-        if long_rows.any():
-            assert cos[long_rows].min() >= COS_TOL, (cos, lens)
-        assert cos[nonempty].min() >= COS_TOL_BF16_SHORT, (cos, lens)
+    assert cos[nonempty].min() >= COS_TOL, (dtype, cos, lens)
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
-@pytest.mark.parametrize("name", ["encode_tiny_2layer.npz", "encode_mpnet_base_b4_s32.npz"])
+@pytest.mark.parametrize("name", ["encode_tiny_2layer.npz", "encode_mpnet_base_b4_s32.npz", "encode_heavy_tail_b10_s96.npz"])
 def test_golden_fixtures(cuda, dtype, name):
+    """Committed vectors minted from transformers.MPNetModel (tools/make_golden.py). The heavy-tail
+    fixture stands in for trained weights: outlier channels x20, LayerNorm gains up to 5, a
+    relative-position table spread over +-8, rows of 1..96 tokens."""
     fx = np.load(os.path.join(GOLDEN, name))
     a = fx["arch"].tolist()
     arch = MPNetArch(vocab_size=a[0], max_position_embeddings=a[1], hidden_size=a[2], num_layers=a[3], num_heads=a[4],
                      intermediate_size=a[5], relative_attention_num_buckets=a[6], pad_token_id=a[7],
                      layer_norm_eps=float(fx["layer_norm_eps"]))
-    enc = _encoder(arch, synthetic_state_dict(arch, int(fx["weight_seed"])), dtype, max_batch=8, max_seq=64)
+    heavy = "heavy_tail" in fx.files and bool(fx["heavy_tail"])
+    sd = (heavy_tail_state_dict if heavy else synthetic_state_dict)(arch, int(fx["weight_seed"]))
+    enc = _encoder(arch, sd, dtype, max_batch=16, max_seq=128)
     got = enc.encode((fx["ids"], fx["mask"]), batch_size=8, normalize_embeddings=True)
     assert got.dtype == np.float32 and got.shape == fx["embeddings"].shape
     _assert_parity(got, fx["embeddings"], fx["mask"], dtype)
@@ -127,7 +125,59 @@ def test_layernorm_fold_matches_unfolded_path(cuda, full_model, dtype, monkeypat
         _assert_parity(outs[-1], ref, mask, dtype)
         enc.close()
     # two independent 16-bit computations: same order of agreement as each has with the oracle
-    assert _cos(outs[0], outs[1]).min() >= (COS_TOL_BF16_SHORT if dtype == "bf16" else 0.99999)
+    assert _cos(outs[0], outs[1]).min() >= (COS_TOL if dtype == "bf16" else 0.99999)
+
+
+def test_pure_bf16_budget(cuda, full_model):
+    """The A/B baseline (bf16 weights and activations, no short-row routing): full rows hold
+    0.9999, rows of a few tokens do not (>= 0.9995) — which is why it is not the shipped mode."""
+    arch, sd, model = full_model
+    ids, mask = eo.synthetic_tokens(12, 100, seed=11)
+    ref = eo.oracle_encode(model, ids, mask)
+    enc = _encoder(arch, sd, "bf16_pure", max_batch=16, max_seq=128)
+    assert enc.short_seq == 0
+    cos = _cos(enc.encode((ids, mask), batch_size=16), ref)
+    lens = mask.sum(1)
+    assert cos[lens >= 32].min() >= COS_TOL and cos.min() >= 0.9995, (cos, lens)
+    enc.close()
+
+
+def test_short_batches_run_in_fp16(cuda, full_model):
+    """dtype='bf16': a batch padded to fewer than `short_seq` tokens is computed with fp16
+    activations by the library itself (same weights) — bit-identical to an fp16 handle; and
+    `encode` never lets a short row share a batch with a long one."""
+    import torch
+
+    arch, sd, model = full_model
+    ids, mask = eo.synthetic_tokens(6, 20, seed=23)
+    d_ids, d_mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    e_mixed = _encoder(arch, sd, "bf16", max_batch=8, max_seq=64)
+    e_f16 = _encoder(arch, sd, "fp16", max_batch=8, max_seq=64)
+    assert e_mixed.short_seq == 32 and e_f16.short_seq == 0
+    assert torch.equal(e_mixed.encode_tokens(d_ids, d_mask), e_f16.encode_tokens(d_ids, d_mask))
+    lengths = np.array([40, 3, 64, 31, 32, 1, 0])
+    order = np.argsort(-lengths, kind="stable")
+    batches = list(e_mixed._batches(order, lengths, 4))
+    assert [sorted(lengths[b].tolist()) for b in batches] == [[32, 40, 64], [0, 1, 3, 31]]
+    e_mixed.close()
+    e_f16.close()
+
+
+def test_out_of_range_token_id_raises(cuda, full_model):
+    """torch's embedding raises on an id outside the vocabulary; here the kernel flags it and
+    `encode` raises after the batch (device flag -> ARB_ERR_INVALID), instead of clamping silently."""
+    from arxiv_rag_b200._lib import ArbError
+
+    arch, sd, _ = full_model
+    enc = _encoder(arch, sd, "bf16", max_batch=4, max_seq=64)
+    ids, mask = eo.synthetic_tokens(3, 40, seed=3)
+    enc.encode((ids, mask))  # clean batch: no error
+    bad = ids.copy()
+    bad[1, 5] = arch.vocab_size + 17
+    with pytest.raises(ArbError, match="outside the vocabulary"):
+        enc.encode((bad, mask))
+    enc.encode((ids, mask))  # the status is cleared by the raise
+    enc.close()
 
 
 def test_eps_is_a_parameter(cuda):

@@ -182,27 +182,31 @@ def test_gemm_schedules_agree_bitwise(lib, cuda):
     assert torch.equal(out[0], out[1])
 
 
-@pytest.mark.parametrize("dt", ["bf16", "fp16"])
-@pytest.mark.parametrize("shape", [(128, 768, 768), (1000, 768, 3072), (333, 256, 128), (5000, 1024, 768)])
-def test_gemm_residual_layernorm_cluster(lib, cuda, dt, shape):
-    """LayerNorm(A.B^T + bias + R) in one kernel: a cluster of N/256 CTAs per row block exchanges
-    the row statistics through distributed shared memory (post-LN of modeling_mpnet.py:210/:242)."""
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("shape", [(300, 256, 768), (4099, 2304, 768), (513, 768, 3072)])
+def test_gemm_mixed_operand_formats(lib, cuda, mode, shape):
+    """ARB_DTYPE_BF16_WF16: A (activations) bf16 x B (weights) fp16 in one tcgen05.mma — the
+    instruction descriptor carries the two formats separately. Products of a bf16 and an fp16 value
+    are exact in fp32, so the fp32-output main loop must match torch to summation order; the 16-bit
+    epilogues write bf16."""
     M, N, K = shape
-    tdt, code, _ = DT[dt]
-    torch.manual_seed(7)
-    A = (torch.randn(M, K, device=cuda) * 0.3).to(tdt)
-    B = (torch.randn(N, K, device=cuda) * 0.05).to(tdt)
-    bias = torch.randn(N, device=cuda)
-    R = (torch.randn(M, N, device=cuda) * 2 + 0.3).to(tdt)
-    g = torch.randn(N, device=cuda) * 0.1 + 1
-    b = torch.randn(N, device=cuda) * 0.1
-    C = torch.zeros(M, N, device=cuda, dtype=tdt)
-    _lib.check(lib.arb_gemm16_residual_ln(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, bias.data_ptr(), R.data_ptr(), N,
-                                          g.data_ptr(), b.data_ptr(), 1e-5, M, N, K, code, _stream()))
-    ref = torch.nn.functional.layer_norm(A.float() @ B.float().T + bias + R.float(), (N,), g, b, 1e-5)
-    assert _rel_err(C, ref) < (8e-3 if dt == "bf16" else 1e-3)
-    assert lib.arb_gemm16_residual_ln(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), 96, bias.data_ptr(), R.data_ptr(), N,
-                                      g.data_ptr(), b.data_ptr(), 1e-5, M, 96, K, code, _stream()) == -1  # N % 256 != 0
+    torch.manual_seed(11)
+    A = (torch.randn(M, K, device=cuda) * 0.5).to(torch.bfloat16)
+    B = (torch.randn(N, K, device=cuda) * 0.5).to(torch.float16)
+    ref = A.float() @ B.float().T
+    _lib.check(lib.arb_set_gemm_mode(mode))
+    try:
+        C = torch.full((M, N), float("nan"), device=cuda)
+        _lib.check(lib.arb_gemm16_f32out(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, M, N, K,
+                                         _lib.ARB_DTYPE_BF16_WF16, _stream()))
+        assert _rel_err(C, ref) < 2e-5
+        bias = torch.randn(N, device=cuda)
+        C16 = torch.zeros(M, N, device=cuda, dtype=torch.bfloat16)
+        _lib.check(lib.arb_gemm16(A.data_ptr(), K, B.data_ptr(), K, C16.data_ptr(), N, bias.data_ptr(), 0, N, M, N, K, 1,
+                                  _lib.ARB_DTYPE_BF16_WF16, _stream()))
+        assert _rel_err(C16, torch.nn.functional.gelu(ref + bias)) < 6e-3
+    finally:
+        _lib.check(lib.arb_set_gemm_mode(0))
 
 
 def test_gemm_strided_operands(lib, cuda):

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from arxiv_rag_b200.weights import ALL_MPNET_BASE_V2, MPNetArch, synthetic_state_dict
+from arxiv_rag_b200.weights import ALL_MPNET_BASE_V2, MPNetArch, heavy_tail_state_dict, synthetic_state_dict
 from oracle import encode_oracle as eo
 from tests.conftest import GOLDEN
 
@@ -18,17 +18,18 @@ def _arch_from_fixture(fx) -> MPNetArch:
                      pad_token_id=a[7], layer_norm_eps=float(fx["layer_norm_eps"]))
 
 
-@pytest.mark.parametrize("name", ["encode_tiny_2layer.npz", "encode_mpnet_base_b4_s32.npz"])
+@pytest.mark.parametrize("name", ["encode_tiny_2layer.npz", "encode_mpnet_base_b4_s32.npz", "encode_heavy_tail_b10_s96.npz"])
 def test_restatement_matches_golden(name):
     """The golden vectors were produced by transformers.MPNetModel; the independent restatement
     must reproduce them from the seed alone (fp32, tolerance 2e-6 abs on unit vectors)."""
     fx = np.load(os.path.join(GOLDEN, name))
     arch = _arch_from_fixture(fx)
-    sd = synthetic_state_dict(arch, int(fx["weight_seed"]))
+    heavy = "heavy_tail" in fx.files and bool(fx["heavy_tail"])
+    sd = (heavy_tail_state_dict if heavy else synthetic_state_dict)(arch, int(fx["weight_seed"]))
     emb, hidden = eo.restated_forward(arch, sd, fx["ids"], fx["mask"], return_hidden=True)
-    assert np.abs(emb - fx["embeddings"]).max() < 2e-6
+    assert np.abs(emb - fx["embeddings"]).max() < (2e-5 if heavy else 2e-6)  # outlier channels x20: fp32 order effects
     valid = fx["mask"][0].astype(bool)
-    assert np.abs(hidden[0][valid] - fx["hidden_row0"][valid]).max() < 2e-4
+    assert np.abs(hidden[0][valid] - fx["hidden_row0"][valid]).max() < (5e-3 if heavy else 2e-4)
     assert np.allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-6)
 
 
@@ -92,6 +93,30 @@ def test_padding_does_not_change_valid_rows():
     mask2 = np.concatenate([mask, np.zeros((3, 7), np.int32)], 1)
     b = eo.restated_forward(arch, sd, ids2, mask2)
     assert np.abs(a - b).max() < 2e-6
+
+
+def test_mixed_format_budget_documented():
+    """DESIGN.md 'Numerics', tools/rounding_budget.py (a CPU model of the folded-LayerNorm schedule
+    with independent formats for weights / activations): bf16 activations x fp16 weights keeps
+    every row of >= 8 tokens above 0.99995, while all-bf16 sits near 0.99993 — the weights'
+    rounding is the part that does not average out over tokens."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("rounding_budget", os.path.join(os.path.dirname(GOLDEN), "..", "tools", "rounding_budget.py"))
+    rb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rb)
+    arch = MPNetArch(vocab_size=1000, num_layers=12)
+    sd = synthetic_state_dict(arch, 0)
+    lengths = np.array([8, 16, 24, 32])
+    ids, mask = eo.synthetic_tokens(4, 32, vocab_size=1000, seed=3)
+    mask = (np.arange(32)[None, :] < lengths[:, None]).astype(np.int32)
+    ids = np.where(mask == 1, ids, 1)
+    ref = eo.restated_forward(arch, sd, ids, mask)
+    mixed = rb.forward(arch, sd, ids, mask, w="fp16", a="bf16", p="bf16")
+    pure = rb.forward(arch, sd, ids, mask, w="bf16", a="bf16", p="bf16")
+    assert (mixed * ref).sum(1).min() >= 0.99995
+    assert (pure * ref).sum(1).min() >= 0.9999
+    assert (mixed * ref).sum(1).mean() > (pure * ref).sum(1).mean()
 
 
 def test_bf16_rounding_budget_documented():

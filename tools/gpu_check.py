@@ -77,6 +77,17 @@ def stage_gemm():
             torch.cuda.synchronize()
             ref = A.float() @ B.float().T
             ok &= report(f"gemm_f32out {d} M{M} N{N} K{K}", C, ref, 2e-5)
+    # mixed operand formats: bf16 activations x fp16 weights (ARB_DTYPE_BF16_WF16)
+    for mode in (1, 2):
+        _lib.check(lib().arb_set_gemm_mode(mode))
+        for (M, N, K) in [(128, 256, 64), (300, 256, 768), (4099, 2304, 768)]:
+            A = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16)
+            B = (torch.randn(N, K, device=DEV) * 0.5).to(torch.float16)
+            C = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
+            _lib.check(lib().arb_gemm16_f32out(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, M, N, K, _lib.ARB_DTYPE_BF16_WF16, stream()))
+            torch.cuda.synchronize()
+            ok &= report(f"gemm_f32out bf16 x fp16 mode{mode} M{M} N{N} K{K}", C, A.float() @ B.float().T, 2e-5)
+    _lib.check(lib().arb_set_gemm_mode(0))
     # epilogues
     for d in ("bf16", "fp16"):
         M, N, K = 777, 768, 768
@@ -92,27 +103,6 @@ def stage_gemm():
                                         R.data_ptr() if epi == 2 else 0, N, M, N, K, epi, dcode(d), stream()))
             torch.cuda.synchronize()
             ok &= report(f"gemm_{name} {d}", C, ref, 6e-3 if d == "bf16" else 8e-4)
-    return ok
-
-
-def stage_gemmln():
-    """Cluster GEMM with fused bias + residual + LayerNorm (DSMEM row statistics)."""
-    ok = True
-    torch.manual_seed(7)
-    for d in ("bf16", "fp16"):
-        for (M, N, K) in [(128, 768, 768), (1000, 768, 3072), (333, 256, 128), (5000, 1024, 768), (70000, 768, 768)]:
-            A = (torch.randn(M, K, device=DEV) * 0.3).to(tdtype(d))
-            B = (torch.randn(N, K, device=DEV) * 0.05).to(tdtype(d))
-            bias = torch.randn(N, device=DEV)
-            R = (torch.randn(M, N, device=DEV) * 2 + 0.3).to(tdtype(d))
-            g = torch.randn(N, device=DEV) * 0.1 + 1
-            b = torch.randn(N, device=DEV) * 0.1
-            C = torch.zeros(M, N, device=DEV, dtype=tdtype(d))
-            _lib.check(lib().arb_gemm16_residual_ln(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, bias.data_ptr(), R.data_ptr(), N,
-                                                    g.data_ptr(), b.data_ptr(), 1e-5, M, N, K, dcode(d), stream()))
-            torch.cuda.synchronize()
-            ref = torch.nn.functional.layer_norm(A.float() @ B.float().T + bias + R.float(), (N,), g, b, 1e-5)
-            ok &= report(f"gemm_residual_ln {d} M{M} N{N} K{K}", C, ref, 8e-3 if d == "bf16" else 1e-3)
     return ok
 
 
@@ -235,11 +225,11 @@ def stage_encode():
         model = eo.reference_model(arch, sd)
         ids, mask = eo.synthetic_tokens(n, S, vocab_size=arch.vocab_size, seed=1)
         ref = eo.oracle_encode(model, ids, mask)
-        for d in ("bf16", "fp16"):
+        for d in ("bf16", "fp16", "bf16_pure"):
             enc = B200SentenceEncoder(sd, arch=arch, max_batch=16, max_seq=128, dtype=d)
             got = enc.encode((ids, mask), batch_size=16, normalize_embeddings=True)
             cos = (got * ref).sum(1)
-            good = bool(np.isfinite(got).all()) and cos.min() >= (0.9999 if d == "fp16" else 0.9995)
+            good = bool(np.isfinite(got).all()) and cos.min() >= (0.9995 if d == "bf16_pure" else 0.9999)
             print(f"[{'OK ' if good else 'BAD'}] encode {name} {d}: cos min {cos.min():.6f} mean {cos.mean():.6f} "
                   f"lens {mask.sum(1).tolist()} cos {np.round(cos, 6).tolist()}", flush=True)
             ok &= good
@@ -275,19 +265,6 @@ def stage_perf():
         ms_cublas = _time(lambda: torch.matmul(A, B.T, out=C))
         fl = 2.0 * M * N * K
         print(f"gemm M{M} N{N} K{K} epi{epi}: {ms:.3f} ms {fl / ms / 1e9:.1f} TFLOP/s | cuBLAS(no epi) {ms_cublas:.3f} ms {fl / ms_cublas / 1e9:.1f} TFLOP/s", flush=True)
-        del A, B, C, R
-    for K in (768, 3072):  # fused bias + residual + LayerNorm cluster GEMM
-        N = 768
-        A = torch.randn(M, K, device=DEV).to(torch.bfloat16)
-        B = (torch.randn(N, K, device=DEV) * 0.05).to(torch.bfloat16)
-        C = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
-        R = torch.randn(M, N, device=DEV).to(torch.bfloat16)
-        bias = torch.randn(N, device=DEV)
-        g = torch.ones(N, device=DEV)
-        ms = _time(lambda: _lib.check(lib().arb_gemm16_residual_ln(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, bias.data_ptr(),
-                                                                   R.data_ptr(), N, g.data_ptr(), bias.data_ptr(), 1e-5, M, N, K,
-                                                                   _lib.ARB_DTYPE_BF16, stream())))
-        print(f"gemm+residual+LN fused M{M} N{N} K{K}: {ms:.3f} ms {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
         del A, B, C, R
     # attention + row ops at the same size
     B_, S, H = 1024, 384, 768
@@ -444,7 +421,7 @@ def stage_searchperf():
     return True
 
 
-STAGES = {"foldperf": stage_foldperf, "gemm2": stage_gemm2, "searchperf": stage_searchperf, "gemm": stage_gemm, "gemmln": stage_gemmln, "rowops": stage_rowops, "attention": stage_attention, "search": stage_search,
+STAGES = {"foldperf": stage_foldperf, "gemm2": stage_gemm2, "searchperf": stage_searchperf, "gemm": stage_gemm, "rowops": stage_rowops, "attention": stage_attention, "search": stage_search,
           "encode": stage_encode, "perf": stage_perf}
 
 if __name__ == "__main__":

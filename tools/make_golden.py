@@ -20,7 +20,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from arxiv_rag_b200.weights import ALL_MPNET_BASE_V2, MPNetArch, synthetic_state_dict  # noqa: E402
+from arxiv_rag_b200.weights import ALL_MPNET_BASE_V2, MPNetArch, heavy_tail_state_dict, synthetic_state_dict  # noqa: E402
 from oracle import encode_oracle as eo  # noqa: E402
 from oracle import search_oracle as so  # noqa: E402
 
@@ -35,17 +35,22 @@ def weights_digest(sd: dict) -> str:
     return h.hexdigest()
 
 
-def make_encode(name: str, arch: MPNetArch, seed: int, n: int, S: int, tok_seed: int):
-    sd = synthetic_state_dict(arch, seed)
+def make_encode(name: str, arch: MPNetArch, seed: int, n: int, S: int, tok_seed: int, heavy: bool = False,
+                lengths=None):
+    sd = heavy_tail_state_dict(arch, seed) if heavy else synthetic_state_dict(arch, seed)
     model = eo.reference_model(arch, sd)  # transformers.MPNetModel, fp32
     ids, mask = eo.synthetic_tokens(n, S, vocab_size=arch.vocab_size, seed=tok_seed)
+    if lengths is not None:  # explicit row lengths (short rows are where 16-bit arithmetic is weakest)
+        lengths = np.asarray(lengths)
+        mask = (np.arange(S)[None, :] < lengths[:, None]).astype(np.int32)
+        ids = np.where(mask == 1, ids, arch.pad_token_id).astype(np.int32)
     emb = eo.oracle_encode(model, ids, mask)
     with torch.no_grad():
         hidden = model(input_ids=torch.from_numpy(ids).long(), attention_mask=torch.from_numpy(mask).long())[0].numpy()
     np.savez_compressed(
         os.path.join(OUT, name), ids=ids, mask=mask, embeddings=emb.astype(np.float32),
         hidden_row0=hidden[0].astype(np.float32), weight_seed=seed, token_seed=tok_seed,
-        weights_sha256=weights_digest(sd),
+        weights_sha256=weights_digest(sd), heavy_tail=heavy,
         arch=np.array([arch.vocab_size, arch.max_position_embeddings, arch.hidden_size, arch.num_layers,
                        arch.num_heads, arch.intermediate_size, arch.relative_attention_num_buckets,
                        arch.pad_token_id]),
@@ -72,6 +77,10 @@ if __name__ == "__main__":
     tiny = MPNetArch(vocab_size=1000, num_layers=2)
     make_encode("encode_tiny_2layer.npz", tiny, seed=0, n=3, S=16, tok_seed=5)
     make_encode("encode_mpnet_base_b4_s32.npz", ALL_MPNET_BASE_V2, seed=0, n=4, S=32, tok_seed=7)
+    # heavy-tailed stand-in for trained weights (outlier channels, wide relative-position table,
+    # large LayerNorm gains), rows of 1..96 tokens
+    make_encode("encode_heavy_tail_b10_s96.npz", ALL_MPNET_BASE_V2, seed=0, n=10, S=96, tok_seed=11, heavy=True,
+                lengths=[96, 1, 2, 3, 5, 9, 17, 33, 64, 80])
     make_search("search_64x32_k5.npz", Q=8, N=64, D=32, k=5, bf16=False, store_data=True)
     make_search("search_2000x768_k10_bf16.npz", Q=16, N=2000, D=768, k=10, bf16=True, store_data=False)
     make_search("search_2000x768_k10_f32.npz", Q=16, N=2000, D=768, k=10, bf16=False, store_data=False)
