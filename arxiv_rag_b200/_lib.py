@@ -17,7 +17,7 @@ LIB_PATH = Path(os.environ.get("ARB_LIB_PATH") or
 ARB_DTYPE_F32 = 0
 ARB_DTYPE_BF16 = 1
 ARB_DTYPE_F16 = 2
-ARB_DTYPE_BF16_WF16 = 3  # bf16 activations x fp16 weights: the shipped "bf16" mode
+ARB_DTYPE_BF16_PURE = 3  # encoder handles: bf16 without the short-batch fp16 path (A/B baseline)
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 
 

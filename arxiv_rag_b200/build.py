@@ -32,11 +32,17 @@ def _stale(target: Path, deps: list[Path]) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | None = None,
-          debug: bool = False) -> Path:
+          debug: bool = False, variant: str | None = None) -> Path:
     """debug=True builds lib/libarxiv_rag_b200_dbg.so with -DARB_HANG_GUARD: a stuck mbarrier
-    wait traps (with a printf) instead of spinning forever — used for first runs of new kernels."""
+    wait traps (with a printf) instead of spinning forever — used for first runs of new kernels.
+    variant='name' builds lib/libarxiv_rag_b200_<name>.so with `extra_flags` (A/B builds selected at
+    run time through ARB_LIB_PATH)."""
     global OBJDIR, LIB
-    if debug:
+    if variant:
+        OBJDIR = PKG / "build" / f"variant_{variant}"
+        OBJDIR.mkdir(parents=True, exist_ok=True)
+        LIB = LIBDIR / f"libarxiv_rag_b200_{variant}.so"
+    elif debug:
         OBJDIR = PKG / "build_dbg"
         LIB = LIBDIR / "libarxiv_rag_b200_dbg.so"
         extra_flags = (extra_flags or []) + ["-DARB_HANG_GUARD"]
@@ -65,7 +71,9 @@ def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | N
     with ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
         objs = list(ex.map(compile_one, sources))
     if force or _stale(LIB, objs):
-        cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *map(str, objs), "-cudart", "static"]
+        # shared cudart: the process already has one (torch's), and a static copy would carry the
+        # runtime's whole entry-point table into the shipped artifact
+        cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *map(str, objs), "-cudart", "shared"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
@@ -73,5 +81,8 @@ def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | N
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv)
+    variant = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")), None)
+    flags = [a for a in sys.argv[1:] if a.startswith("-D")]
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv,
+                 variant=variant, extra_flags=flags or None)
     print(path)

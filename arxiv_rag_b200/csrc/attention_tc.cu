@@ -20,6 +20,8 @@
 // 8-byte loads.
 // TMEM: S[0] cols 0..191, S[1] 192..383, O[0] 384..447, O[1] 448..511 (all 512 columns).
 // Smem: K and V of the head double-buffered across items (TMA, 128-byte swizzle), one Q tile.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tmap.cuh"
@@ -166,7 +168,15 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, int nchunk, float scal
     l_out = l;
 }
 
-template <bool kF16>
+// kDefer: which softmax group combines the two key halves and stores the tile.
+//   false  group 0 does, right after its own softmax — it then waits for group 1's half of the same
+//          tile, which keeps the two groups in lockstep (both in the TMEM-read/max pass together,
+//          both in the MUFU pass together, both idle during the PV -> QK turnaround);
+//   true   group 0 only publishes its (shift, row sum) and moves on to the next tile; group 1
+//          combines after its own softmax, inside the wait for its next score tile. The MMA warp
+//          serves the groups alternately, so they settle into a stagger: one group's exp2 pass
+//          overlaps the other's turnaround and max pass.
+template <bool kF16, bool kDefer>
 __global__ void __launch_bounds__(kAtThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                     const float* __restrict__ rel_bias, int max_rel, const int32_t* __restrict__ mask,
@@ -184,7 +194,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint64_t* p_ready = bars + 8;    // [2]
     uint64_t* o_full = bars + 10;    // [2]
     uint64_t* o_free = bars + 12;
-    uint64_t* ml_ready = bars + 13;
+    uint64_t* ml_ready = bars + 13;  // [2], by tile parity: a slot is reused two tiles later, after its combine
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
     const int warp = __shfl_sync(0xffffffff, threadIdx.x / 32, 0);
@@ -236,7 +246,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         mbar_init(q_full, 1);
         mbar_init(q_empty, 1);
         mbar_init(o_free, 128);
-        mbar_init(ml_ready, 128);
+        mbar_init(ml_ready + 0, 128);
+        mbar_init(ml_ready + 1, 128);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -402,18 +413,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(p_ready + hh);
-                if (hh == 1) {
+                constexpr int kCombiner = kDefer ? 1 : 0;
+                if (hh != kCombiner) {
                     exch[ph * kAtQT + r] = make_float2(c, l);
-                    mbar_arrive(ml_ready);  // release: the smem write above is ordered before the arrive
+                    mbar_arrive(ml_ready + ph);  // release: the smem write above is ordered before the arrive
                     continue;
                 }
-                // ---- group 0: combine the halves, normalise, store this row of ctx
-                mbar_wait(ml_ready, ph);
+                // ---- combining group: merge the halves, normalise, store this row of ctx
+                mbar_wait(ml_ready + ph, (g >> 1) & 1);
                 const float2 e1 = exch[ph * kAtQT + r];
                 const float m = fmaxf(c, e1.x);
-                const float a0 = at_exp2(c - m), a1 = at_exp2(e1.x - m);
-                const float inv = __fdividef(1.f, a0 * l + a1 * e1.y);
-                const float w0 = a0 * inv, w1 = a1 * inv;
+                const float a_mine = at_exp2(c - m), a_other = at_exp2(e1.x - m);
+                const float inv = __fdividef(1.f, a_mine * l + a_other * e1.y);
+                const float w0 = (kCombiner == 0 ? a_mine : a_other) * inv;  // weight of O[0]
+                const float w1 = (kCombiner == 0 ? a_other : a_mine) * inv;  // weight of O[1]
                 const uint32_t tO = tmem + lane_sel + kAtColO;
                 mbar_wait(o_full + 0, ph);
                 mbar_wait(o_full + 1, ph);
@@ -473,7 +486,13 @@ int launch_attention_tc(const h16* qkv, const float* rel_bias, int max_rel, cons
         set_error("attention_tc: cuTensorMapEncodeTiled failed");
         return ARB_ERR_CUDA;
     }
-    auto kern = fp16 ? attention_tc_kernel<true> : attention_tc_kernel<false>;
+    // ARB_ATTN_DEFER=0 selects the lockstep schedule (group 0 combines) for A/B runs
+    static const bool defer = []() {
+        const char* e = getenv("ARB_ATTN_DEFER");
+        return !(e && e[0] == '0');
+    }();
+    auto kern = fp16 ? (defer ? attention_tc_kernel<true, true> : attention_tc_kernel<true, false>)
+                     : (defer ? attention_tc_kernel<false, true> : attention_tc_kernel<false, false>);
     ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int ngroups = num_sms() / heads;
     if (ngroups < 1) ngroups = 1;

@@ -26,14 +26,12 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
-// public 16-bit dtype code -> operand formats of a launch (kernels.h FMT_*)
-static int dtype16(int32_t dtype, int* fmt) {
-    ARB_REQUIRE(dtype == ARB_DTYPE_BF16 || dtype == ARB_DTYPE_F16 || dtype == ARB_DTYPE_BF16_WF16,
-                "dtype %d must be ARB_DTYPE_BF16, ARB_DTYPE_F16 or ARB_DTYPE_BF16_WF16", dtype);
-    *fmt = dtype == ARB_DTYPE_F16 ? (FMT_ACT_F16 | FMT_W_F16) : dtype == ARB_DTYPE_BF16_WF16 ? FMT_W_F16 : 0;
+// public 16-bit dtype code of the kernel-level entry points -> fp16 flag
+static int dtype16(int32_t dtype, bool* fp16) {
+    ARB_REQUIRE(dtype == ARB_DTYPE_BF16 || dtype == ARB_DTYPE_F16, "dtype %d must be ARB_DTYPE_BF16 or ARB_DTYPE_F16", dtype);
+    *fp16 = dtype == ARB_DTYPE_F16;
     return ARB_OK;
 }
-
 
 // ---- MPNetEncoder.relative_position_bucket (modeling_mpnet.py:343-360), float32 like torch.
 static int relative_bucket(int relative_position, int num_buckets, int max_distance) {
@@ -71,13 +69,14 @@ struct Mpnet {
     std::vector<void*> allocs;
     float *word_emb = nullptr, *pos_emb = nullptr, *emb_g = nullptr, *emb_b = nullptr;
     float* rel_bias = nullptr;  // [heads, 2*max_seq-1], entry r <-> j-i = r-(max_seq-1)
-    std::vector<LayerDev> layers;
+    std::vector<LayerDev> layers;     // weights in the handle's 16-bit format
+    std::vector<LayerDev> layers_f16; // bf16 handles: an fp16 copy for short batches (see short_f16)
     h16 *h = nullptr, *h1 = nullptr, *tmp = nullptr, *ctx = nullptr, *qkv = nullptr, *ffn = nullptr;
-    int fmt = 0;           // FMT_ACT_F16 | FMT_W_F16 (kernels.h): 16-bit formats of activations / weights
-    // compute_dtype ARB_DTYPE_BF16_WF16: batches padded to fewer than kShortSeq tokens run with
-    // fp16 activations (same fp16 weights, same buffers). A row of a few tokens has no mean-pool
-    // averaging over its bf16 activation noise and cannot reach cosine 0.9999 otherwise
-    // (tools/rounding_budget.py); such values are far inside the fp16 range after the LayerNorms.
+    bool fp16 = false;     // 16-bit format of weights + activations (one format per tcgen05 MMA)
+    // compute_dtype ARB_DTYPE_BF16: batches padded to fewer than kShortSeq tokens run in fp16 (an
+    // fp16 copy of the weights, the same activation buffers). A row of a few tokens has no
+    // mean-pool averaging over its bf16 rounding noise and cannot reach cosine 0.9999 otherwise
+    // (tools/rounding_budget.py). ARB_DTYPE_BF16_PURE switches this off (A/B baseline).
     bool short_f16 = false;
     int* status_host = nullptr;  // host-mapped status word [0]=error, [1]=token id, [2]=token index
     int* status_dev = nullptr;
@@ -102,10 +101,10 @@ struct Mpnet {
         return ARB_OK;
     }
     // fp32 host values -> 16-bit (round-to-nearest-even) device
-    int upload16(h16* dst, const float* src, size_t count) {
+    int upload16(h16* dst, const float* src, size_t count, bool f16) {
         ARB_REQUIRE(src != nullptr, "mpnet_create: missing weight matrix");
         std::vector<h16> tmpv(count);
-        if (fmt_w_f16(fmt)) {
+        if (f16) {
             for (size_t i = 0; i < count; ++i) tmpv[i] = __half_as_ushort(__float2half_rn(src[i]));
         } else {
             for (size_t i = 0; i < count; ++i) tmpv[i] = __bfloat16_as_ushort(__float2bfloat16_rn(src[i]));
@@ -116,7 +115,7 @@ struct Mpnet {
     // W'[n,k] = W[n,k] * gamma[k] rounded to 16 bit -> dst; colsum[n] = sum_k W'[n,k] (of the ROUNDED
     // values, so that x W'^T - mean * colsum cancels exactly); bias_out[n] = bias[n] + sum_k W[n,k] beta[k]
     int upload16_folded(h16* dst, float* colsum_dev, float* bias_dev, const float* w, const float* bias,
-                        const float* gamma, const float* beta, size_t N, size_t K) {
+                        const float* gamma, const float* beta, size_t N, size_t K, bool f16) {
         ARB_REQUIRE(w && bias && gamma && beta, "mpnet_create: missing weight array");
         std::vector<h16> t16(N * K);
         std::vector<float> cs(N), bo(N);
@@ -125,7 +124,7 @@ struct Mpnet {
             for (size_t k = 0; k < K; ++k) {
                 const float wf = w[n * K + k] * gamma[k];
                 float back;
-                if (fmt_w_f16(fmt)) {
+                if (f16) {
                     const __half hv = __float2half_rn(wf);
                     t16[n * K + k] = __half_as_ushort(hv);
                     back = __half2float(hv);
@@ -151,6 +150,8 @@ struct Mpnet {
     }
 };
 
+static int mpnet_build_layers(Mpnet* m, const ArbMpnetWeights* w, std::vector<LayerDev>& layers, bool f16);
+
 static int mpnet_build(Mpnet* m, const ArbMpnetWeights* w) {
     const ArbMpnetConfig& c = m->cfg;
     const size_t H = c.hidden_size, I = c.intermediate_size;
@@ -171,52 +172,9 @@ static int mpnet_build(Mpnet* m, const ArbMpnetWeights* w) {
         }
         if (int rc = m->upload_f32(&m->rel_bias, tbl.data(), tbl.size())) return rc;
     }
-    m->layers.resize(c.num_layers);
-    for (int l = 0; l < c.num_layers; ++l) {
-        const ArbMpnetLayerWeights& lw = w->layers[l];
-        LayerDev& d = m->layers[l];
-        if (int rc = m->alloc(&d.w_qkv, 3 * H * H)) return rc;
-        if (int rc = m->alloc(&d.b_qkv, 3 * H)) return rc;
-        ARB_REQUIRE(lw.q_b && lw.k_b && lw.v_b, "mpnet_create: missing q/k/v bias (layer %d)", l);
-        if (m->fold_ln && l > 0) {
-            // the q/k/v projections of layer l read LN2 of layer l-1: carry its gamma/beta
-            const ArbMpnetLayerWeights& pw = w->layers[l - 1];
-            if (int rc = m->alloc(&d.c_qkv, 3 * H)) return rc;
-            const float* ws[3] = {lw.q_w, lw.k_w, lw.v_w};
-            const float* bs[3] = {lw.q_b, lw.k_b, lw.v_b};
-            for (int t = 0; t < 3; ++t)
-                if (int rc = m->upload16_folded(d.w_qkv + t * H * H, d.c_qkv + t * H, d.b_qkv + t * H, ws[t], bs[t],
-                                                pw.out_ln_g, pw.out_ln_b, H, H))
-                    return rc;
-        } else {
-            if (int rc = m->upload16(d.w_qkv, lw.q_w, H * H)) return rc;
-            if (int rc = m->upload16(d.w_qkv + H * H, lw.k_w, H * H)) return rc;
-            if (int rc = m->upload16(d.w_qkv + 2 * H * H, lw.v_w, H * H)) return rc;
-            ARB_CHECK_CUDA(cudaMemcpy(d.b_qkv, lw.q_b, H * 4, cudaMemcpyHostToDevice));
-            ARB_CHECK_CUDA(cudaMemcpy(d.b_qkv + H, lw.k_b, H * 4, cudaMemcpyHostToDevice));
-            ARB_CHECK_CUDA(cudaMemcpy(d.b_qkv + 2 * H, lw.v_b, H * 4, cudaMemcpyHostToDevice));
-        }
-        if (int rc = m->alloc(&d.w_o, H * H)) return rc;
-        if (int rc = m->upload16(d.w_o, lw.o_w, H * H)) return rc;
-        if (int rc = m->upload_f32(&d.b_o, lw.o_b, H)) return rc;
-        if (int rc = m->upload_f32(&d.ln1_g, lw.attn_ln_g, H)) return rc;
-        if (int rc = m->upload_f32(&d.ln1_b, lw.attn_ln_b, H)) return rc;
-        if (int rc = m->alloc(&d.w_in, I * H)) return rc;
-        if (m->fold_ln) {  // the FFN up-projection reads LN1 of this layer
-            if (int rc = m->alloc(&d.c_in, I)) return rc;
-            if (int rc = m->alloc(&d.b_in, I)) return rc;
-            if (int rc = m->upload16_folded(d.w_in, d.c_in, d.b_in, lw.ffn_in_w, lw.ffn_in_b, lw.attn_ln_g, lw.attn_ln_b, I, H))
-                return rc;
-        } else {
-            if (int rc = m->upload16(d.w_in, lw.ffn_in_w, I * H)) return rc;
-            if (int rc = m->upload_f32(&d.b_in, lw.ffn_in_b, I)) return rc;
-        }
-        if (int rc = m->alloc(&d.w_out, H * I)) return rc;
-        if (int rc = m->upload16(d.w_out, lw.ffn_out_w, H * I)) return rc;
-        if (int rc = m->upload_f32(&d.b_out, lw.ffn_out_b, H)) return rc;
-        if (int rc = m->upload_f32(&d.ln2_g, lw.out_ln_g, H)) return rc;
-        if (int rc = m->upload_f32(&d.ln2_b, lw.out_ln_b, H)) return rc;
-    }
+    if (int rc = mpnet_build_layers(m, w, m->layers, m->fp16)) return rc;
+    if (m->short_f16)
+        if (int rc = mpnet_build_layers(m, w, m->layers_f16, true)) return rc;
     const size_t T = static_cast<size_t>(m->max_tokens);
     if (int rc = m->alloc(&m->h, T * H)) return rc;
     if (int rc = m->alloc(&m->h1, T * H)) return rc;
@@ -231,6 +189,59 @@ static int mpnet_build(Mpnet* m, const ArbMpnetWeights* w) {
     return ARB_OK;
 }
 
+// One set of per-layer device weights in the fp16 (f16 = true) or bf16 format.
+static int mpnet_build_layers(Mpnet* m, const ArbMpnetWeights* w, std::vector<LayerDev>& layers, bool f16) {
+    const ArbMpnetConfig& c = m->cfg;
+    const size_t H = c.hidden_size, I = c.intermediate_size;
+    layers.resize(c.num_layers);
+    for (int l = 0; l < c.num_layers; ++l) {
+        const ArbMpnetLayerWeights& lw = w->layers[l];
+        LayerDev& d = layers[l];
+        if (int rc = m->alloc(&d.w_qkv, 3 * H * H)) return rc;
+        if (int rc = m->alloc(&d.b_qkv, 3 * H)) return rc;
+        ARB_REQUIRE(lw.q_b && lw.k_b && lw.v_b, "mpnet_create: missing q/k/v bias (layer %d)", l);
+        if (m->fold_ln && l > 0) {
+            // the q/k/v projections of layer l read LN2 of layer l-1: carry its gamma/beta
+            const ArbMpnetLayerWeights& pw = w->layers[l - 1];
+            if (int rc = m->alloc(&d.c_qkv, 3 * H)) return rc;
+            const float* ws[3] = {lw.q_w, lw.k_w, lw.v_w};
+            const float* bs[3] = {lw.q_b, lw.k_b, lw.v_b};
+            for (int t = 0; t < 3; ++t)
+                if (int rc = m->upload16_folded(d.w_qkv + t * H * H, d.c_qkv + t * H, d.b_qkv + t * H, ws[t], bs[t],
+                                                pw.out_ln_g, pw.out_ln_b, H, H, f16))
+                    return rc;
+        } else {
+            if (int rc = m->upload16(d.w_qkv, lw.q_w, H * H, f16)) return rc;
+            if (int rc = m->upload16(d.w_qkv + H * H, lw.k_w, H * H, f16)) return rc;
+            if (int rc = m->upload16(d.w_qkv + 2 * H * H, lw.v_w, H * H, f16)) return rc;
+            ARB_CHECK_CUDA(cudaMemcpy(d.b_qkv, lw.q_b, H * 4, cudaMemcpyHostToDevice));
+            ARB_CHECK_CUDA(cudaMemcpy(d.b_qkv + H, lw.k_b, H * 4, cudaMemcpyHostToDevice));
+            ARB_CHECK_CUDA(cudaMemcpy(d.b_qkv + 2 * H, lw.v_b, H * 4, cudaMemcpyHostToDevice));
+        }
+        if (int rc = m->alloc(&d.w_o, H * H)) return rc;
+        if (int rc = m->upload16(d.w_o, lw.o_w, H * H, f16)) return rc;
+        if (int rc = m->upload_f32(&d.b_o, lw.o_b, H)) return rc;
+        if (int rc = m->upload_f32(&d.ln1_g, lw.attn_ln_g, H)) return rc;
+        if (int rc = m->upload_f32(&d.ln1_b, lw.attn_ln_b, H)) return rc;
+        if (int rc = m->alloc(&d.w_in, I * H)) return rc;
+        if (m->fold_ln) {  // the FFN up-projection reads LN1 of this layer
+            if (int rc = m->alloc(&d.c_in, I)) return rc;
+            if (int rc = m->alloc(&d.b_in, I)) return rc;
+            if (int rc = m->upload16_folded(d.w_in, d.c_in, d.b_in, lw.ffn_in_w, lw.ffn_in_b, lw.attn_ln_g, lw.attn_ln_b, I, H, f16))
+                return rc;
+        } else {
+            if (int rc = m->upload16(d.w_in, lw.ffn_in_w, I * H, f16)) return rc;
+            if (int rc = m->upload_f32(&d.b_in, lw.ffn_in_b, I)) return rc;
+        }
+        if (int rc = m->alloc(&d.w_out, H * I)) return rc;
+        if (int rc = m->upload16(d.w_out, lw.ffn_out_w, H * I, f16)) return rc;
+        if (int rc = m->upload_f32(&d.b_out, lw.ffn_out_b, H)) return rc;
+        if (int rc = m->upload_f32(&d.ln2_g, lw.out_ln_g, H)) return rc;
+        if (int rc = m->upload_f32(&d.ln2_b, lw.out_ln_b, H)) return rc;
+    }
+    return ARB_OK;
+}
+
 constexpr int kShortSeq = 32;
 
 static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B, int S, float* out,
@@ -238,8 +249,10 @@ static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B
     const ArbMpnetConfig& c = m->cfg;
     const int H = c.hidden_size, I = c.intermediate_size;
     const int64_t T = static_cast<int64_t>(B) * S;
-    const int fmt = m->fmt | ((m->short_f16 && S < kShortSeq) ? FMT_ACT_F16 : 0);
-    const bool a16 = fmt_act_f16(fmt);
+    const bool use_f16_copy = m->short_f16 && S < kShortSeq;
+    const bool a16 = m->fp16 || use_f16_copy;
+    const bool fmt = a16;  // one 16-bit format for every operand of this call
+    const std::vector<LayerDev>& layers = use_f16_copy ? m->layers_f16 : m->layers;
     int rc;
     if ((rc = launch_embed_ln(ids, m->word_emb, m->pos_emb, m->emb_g, m->emb_b, m->h, B, S, H,
                               c.vocab_size, c.max_position_embeddings, c.pad_token_id, c.position_mode,
@@ -253,7 +266,7 @@ static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B
         f.inv_width_in = 1.0f / static_cast<float>(H);
         f.eps = c.layer_norm_eps;
         for (int l = 0; l < c.num_layers; ++l) {
-            const LayerDev& d = m->layers[l];
+            const LayerDev& d = layers[l];
             LnFoldArgs fq = f, fo = f, fu = f, fd = f;
             if (l == 0) {  // the embedding LayerNorm output is already normalised
                 if ((rc = launch_gemm16(m->h, H, d.w_qkv, H, m->qkv, 3 * H, d.b_qkv, nullptr, 0, T, 3 * H, H, EPI_BIAS, fmt, st))) return rc;
@@ -268,8 +281,8 @@ static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B
             if (l == 0) {
                 if ((rc = launch_gemm16_fold(m->ctx, H, d.w_o, H, m->h1, H, d.b_o, m->h, H, T, H, H, EPI_BIAS_RES_STATS, fo, fmt, st))) return rc;
             } else {
-                fo.gamma = m->layers[l - 1].ln2_g;
-                fo.beta = m->layers[l - 1].ln2_b;
+                fo.gamma = layers[l - 1].ln2_g;
+                fo.beta = layers[l - 1].ln2_b;
                 fo.stats_in = m->stats_x;
                 if ((rc = launch_gemm16_fold(m->ctx, H, d.w_o, H, m->h1, H, d.b_o, m->tmp, H, T, H, H, EPI_BIAS_LNRES_STATS, fo, fmt, st))) return rc;
             }
@@ -284,12 +297,12 @@ static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B
             fd.stats_out = m->stats_x;
             if ((rc = launch_gemm16_fold(m->ffn, I, d.w_out, I, m->tmp, H, d.b_out, m->h1, H, T, H, I, EPI_BIAS_LNRES_STATS, fd, fmt, st))) return rc;
         }
-        const LayerDev& last = m->layers[c.num_layers - 1];
+        const LayerDev& last = layers[c.num_layers - 1];
         if ((rc = launch_layernorm(m->tmp, last.ln2_g, last.ln2_b, m->h, T, H, c.layer_norm_eps, a16, st))) return rc;
         return launch_pool_normalize(m->h, mask, out, B, S, H, a16, st);
     }
     for (int l = 0; l < c.num_layers; ++l) {
-        const LayerDev& d = m->layers[l];
+        const LayerDev& d = layers[l];
         // q,k,v projections as one [T,H] x [3H,H]^T GEMM (modeling_mpnet.py:145-159)
         if ((rc = launch_gemm16(m->h, H, d.w_qkv, H, m->qkv, 3 * H, d.b_qkv, nullptr, 0, T, 3 * H, H, EPI_BIAS, fmt, st))) return rc;
         // softmax(qk^T/8 + position_bias + mask) v (:162-177)
@@ -331,8 +344,8 @@ int arb_mpnet_create(const ArbMpnetConfig* cfg, const ArbMpnetWeights* weights, 
     ARB_REQUIRE(cfg->hidden_size % 128 == 0 && cfg->hidden_size <= 1024, "mpnet_create: hidden size %d unsupported", cfg->hidden_size);
     ARB_REQUIRE(cfg->intermediate_size % 32 == 0, "mpnet_create: intermediate size %d unsupported", cfg->intermediate_size);
     ARB_REQUIRE(cfg->compute_dtype == ARB_DTYPE_BF16 || cfg->compute_dtype == ARB_DTYPE_F16 ||
-                    cfg->compute_dtype == ARB_DTYPE_BF16_WF16,
-                "mpnet_create: compute_dtype %d must be ARB_DTYPE_BF16_WF16, ARB_DTYPE_F16 or ARB_DTYPE_BF16", cfg->compute_dtype);
+                    cfg->compute_dtype == ARB_DTYPE_BF16_PURE,
+                "mpnet_create: compute_dtype %d must be ARB_DTYPE_F16, ARB_DTYPE_BF16 or ARB_DTYPE_BF16_PURE", cfg->compute_dtype);
     ARB_REQUIRE(cfg->num_layers > 0 && cfg->vocab_size > 0 && cfg->max_position_embeddings > 2,
                 "mpnet_create: bad layer/vocab/position counts");
     ARB_REQUIRE(max_tokens > 0 && max_seq > 0 && max_seq <= 768, "mpnet_create: bad max_tokens=%lld / max_seq=%d",
@@ -352,11 +365,8 @@ int arb_mpnet_create(const ArbMpnetConfig* cfg, const ArbMpnetWeights* weights, 
     Mpnet* m = new (std::nothrow) Mpnet();
     ARB_REQUIRE(m != nullptr, "mpnet_create: out of host memory");
     m->cfg = *cfg;
-    if (int rc = dtype16(cfg->compute_dtype, &m->fmt)) {
-        delete m;
-        return rc;
-    }
-    m->short_f16 = cfg->compute_dtype == ARB_DTYPE_BF16_WF16;
+    m->fp16 = cfg->compute_dtype == ARB_DTYPE_F16;
+    m->short_f16 = cfg->compute_dtype == ARB_DTYPE_BF16;
     // The LayerNorms are folded into the neighbouring GEMM epilogues
     // (EPI_LNIN_* / EPI_*_STATS, kernels.h). ARB_FOLD_LN=0 keeps the GEMM + LayerNorm-pass path
     // (the A/B baseline; both are parity-tested).
@@ -465,8 +475,8 @@ int arb_gemm16_lnfold(const void* A, int64_t lda, const void* B, int64_t ldb, vo
                       const void* R, int64_t ldr, const float* colsum, const float* gamma, const float* beta,
                       const float* stats_in, int32_t parts_in, int32_t width_in, float* stats_out, float eps, int64_t M,
                       int32_t N, int32_t K, int32_t epilogue, int32_t dtype, void* stream) {
-    int fmt;
-    if (int rc = dtype16(dtype, &fmt)) return rc;
+    bool fp16;
+    if (int rc = dtype16(dtype, &fp16)) return rc;
     LnFoldArgs f;
     f.colsum = colsum;
     f.gamma = gamma;
@@ -477,7 +487,7 @@ int arb_gemm16_lnfold(const void* A, int64_t lda, const void* B, int64_t ldb, vo
     f.inv_width_in = width_in > 0 ? 1.0f / static_cast<float>(width_in) : 0.f;
     f.eps = eps;
     return launch_gemm16_fold(static_cast<const h16*>(A), lda, static_cast<const h16*>(B), ldb, static_cast<h16*>(C), ldc, bias,
-                              static_cast<const h16*>(R), ldr, M, N, K, epilogue, f, fmt, static_cast<cudaStream_t>(stream));
+                              static_cast<const h16*>(R), ldr, M, N, K, epilogue, f, fp16, static_cast<cudaStream_t>(stream));
 }
 
 size_t arb_topk_exchange_bytes(int32_t G, size_t slot_bytes) { return G > 0 ? topk_exchange_bytes(G, slot_bytes) : 0; }
@@ -552,33 +562,27 @@ int arb_topk_merge_records(const void* records_dev, int32_t G, int64_t Q, int32_
 int arb_gemm16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                const float* bias, const void* R, int64_t ldr, int64_t M, int32_t N, int32_t K,
                int32_t epilogue, int32_t dtype, void* stream) {
-    int fmt;
-    if (int rc = dtype16(dtype, &fmt)) return rc;
-    const bool f = fmt_act_f16(fmt);
-    (void)f;
+    bool f;
+    if (int rc = dtype16(dtype, &f)) return rc;
     return launch_gemm16(static_cast<const h16*>(A), lda, static_cast<const h16*>(B), ldb, static_cast<h16*>(C),
-                         ldc, bias, static_cast<const h16*>(R), ldr, M, N, K, epilogue, fmt,
+                         ldc, bias, static_cast<const h16*>(R), ldr, M, N, K, epilogue, f,
                          static_cast<cudaStream_t>(stream));
 }
 
 int arb_gemm16_f32out(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
                       int64_t M, int32_t N, int32_t K, int32_t dtype, void* stream) {
-    int fmt;
-    if (int rc = dtype16(dtype, &fmt)) return rc;
-    const bool f = fmt_act_f16(fmt);
-    (void)f;
+    bool f;
+    if (int rc = dtype16(dtype, &f)) return rc;
     return launch_gemm16_f32out(static_cast<const h16*>(A), lda, static_cast<const h16*>(B), ldb, C, ldc, M, N,
-                                K, fmt, static_cast<cudaStream_t>(stream));
+                                K, f, static_cast<cudaStream_t>(stream));
 }
 
 int arb_embed_layernorm(const int32_t* ids, const float* word_emb, const float* pos_emb,
                         const float* gamma, const float* beta, void* out16, int32_t B, int32_t S,
                         int32_t H, int32_t vocab, int32_t max_pos, int32_t pad_id, int32_t position_mode,
                         float eps, int32_t dtype, void* stream) {
-    int fmt;
-    if (int rc = dtype16(dtype, &fmt)) return rc;
-    const bool f = fmt_act_f16(fmt);
-    (void)f;
+    bool f;
+    if (int rc = dtype16(dtype, &f)) return rc;
     ARB_REQUIRE(position_mode == 0 || position_mode == 1, "embed_layernorm: position_mode %d must be 0 or 1", position_mode);
     return launch_embed_ln(ids, word_emb, pos_emb, gamma, beta, static_cast<h16*>(out16), B, S, H, vocab,
                            max_pos, pad_id, position_mode, eps, f, nullptr, static_cast<cudaStream_t>(stream));
@@ -590,10 +594,8 @@ int arb_adjacent_cosine(const float* emb_dev, int64_t n, int32_t D, float* out_d
 
 int arb_layernorm16(const void* x, const float* gamma, const float* beta, void* out, int64_t rows,
                     int32_t H, float eps, int32_t dtype, void* stream) {
-    int fmt;
-    if (int rc = dtype16(dtype, &fmt)) return rc;
-    const bool f = fmt_act_f16(fmt);
-    (void)f;
+    bool f;
+    if (int rc = dtype16(dtype, &f)) return rc;
     return launch_layernorm(static_cast<const h16*>(x), gamma, beta, static_cast<h16*>(out), rows, H, eps, f,
                             static_cast<cudaStream_t>(stream));
 }
@@ -601,20 +603,16 @@ int arb_layernorm16(const void* x, const float* gamma, const float* beta, void* 
 int arb_attention16(const void* qkv, const float* rel_bias, int32_t max_rel, const int32_t* mask,
                     void* ctx, int32_t B, int32_t S, int32_t heads, int32_t head_dim, int32_t dtype,
                     int32_t impl, void* stream) {
-    int fmt;
-    if (int rc = dtype16(dtype, &fmt)) return rc;
-    const bool f = fmt_act_f16(fmt);
-    (void)f;
+    bool f;
+    if (int rc = dtype16(dtype, &f)) return rc;
     return launch_attention(static_cast<const h16*>(qkv), rel_bias, max_rel, mask, static_cast<h16*>(ctx), B, S,
                             heads, head_dim, f, impl, static_cast<cudaStream_t>(stream));
 }
 
 int arb_pool_normalize(const void* hidden16, const int32_t* mask, float* out, int32_t B, int32_t S,
                        int32_t H, int32_t dtype, void* stream) {
-    int fmt;
-    if (int rc = dtype16(dtype, &fmt)) return rc;
-    const bool f = fmt_act_f16(fmt);
-    (void)f;
+    bool f;
+    if (int rc = dtype16(dtype, &f)) return rc;
     return launch_pool_normalize(static_cast<const h16*>(hidden16), mask, out, B, S, H, f,
                                  static_cast<cudaStream_t>(stream));
 }

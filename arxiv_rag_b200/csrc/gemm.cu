@@ -102,9 +102,36 @@ __device__ __forceinline__ float gelu_tanh_fit(float x) {
     return fmaf(h, t, h);
 }
 
-// kF16 = format of the 16-bit ACTIVATIONS (A, C, R); the weights' format (B) only enters through
-// the instruction descriptor `idesc`, a kernel argument, so bf16 activations x fp16 weights is
-// the same kernel as the uniform-format cases.
+// gelu(x) = x sigmoid(2 u(x)) with u(x) = x (a + b x^2 + c x^4) the minimax fit of atanh(erf(x/sqrt2))
+// (|gelu error| <= 2.6e-5 for every x, 1/10 of the 2-term tanh form) evaluated through ex2 and rcp,
+// whose approximations are good to 2^-22 — unlike MUFU.TANH (2^-11). x^2 is clamped at 50: the
+// quartic term would otherwise turn u around for |x| > 7, where the sigmoid has long saturated.
+// 9 instructions (2 MUFU); candidate for the fp16 mode in place of the 15-instruction erf form.
+__device__ __forceinline__ float gelu_sigmoid_fit3(float x) {
+    constexpr float k = -2.0f * 1.4426950408889634f;  // exp(-2u) = 2^(k u)
+    constexpr float a = 0.797507868f * k, b = 0.03700566f * k, c = -0.000351518939f * k;
+    const float x2 = fminf(x * x, 50.0f);
+    const float w = x * fmaf(x2, fmaf(x2, c, b), a);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(w));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+}
+
+// GELU of the fp16 mode: 0 = erf form, 1 = sigmoid fit, 2 = the bf16 mode's tanh fit (build-time A/B)
+#ifndef ARB_GELU_F16
+#define ARB_GELU_F16 0
+#endif
+__device__ __forceinline__ float gelu_f16_mode(float x) {
+#if ARB_GELU_F16 == 0
+    return gelu_erf(x);
+#elif ARB_GELU_F16 == 1
+    return gelu_sigmoid_fit3(x);
+#else
+    return gelu_tanh_fit(x);
+#endif
+}
+
 // OutT = h16 (16-bit activations in the kF16 format) or float. k2Cta: launched as clusters of two
 // CTAs that share one 256 x 256 tile through tcgen05 cta_group::2 (see umma_pipe.cuh).
 template <int EPI, bool kF16, typename OutT, bool k2Cta>
@@ -298,7 +325,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
                 }
                 if (kGelu) {
 #pragma unroll
-                    for (int j = 0; j < CW; ++j) v[j] = kF16 ? gelu_erf(v[j]) : gelu_tanh_fit(v[j]);
+                    for (int j = 0; j < CW; ++j) v[j] = kF16 ? gelu_f16_mode(v[j]) : gelu_tanh_fit(v[j]);
                 }
                 if (kRes) {
                     mbar_wait(res_bar, (res_phase >> buf) & 1u);
@@ -390,7 +417,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 template <int EPI, bool kF16, typename OutT>
 static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb, OutT* C,
                             int64_t ldc, const float* bias, const h16* R, int64_t ldr, int64_t M,
-                            int N, int K, bool w_fp16, cudaStream_t stream, const LnFoldArgs& fold = LnFoldArgs()) {
+                            int N, int K, cudaStream_t stream, const LnFoldArgs& fold = LnFoldArgs()) {
     constexpr bool kRes = EPI == EPI_BIAS_RESIDUAL || EPI == EPI_BIAS_LNRES_STATS || EPI == EPI_BIAS_RES_STATS;
     CUtensorMap ta, tb, tc, tr;
     // the TMA element type only matters for OOB fill; both 16-bit formats move as raw 2-byte words
@@ -432,7 +459,7 @@ static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        ARB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tr, bias, M, N, K, fold, umma_idesc_16bit(2 * kBM, kGemmBN, kF16, w_fp16)));
+        ARB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tr, bias, M, N, K, fold, umma_idesc_16bit(2 * kBM, kGemmBN, kF16)));
         return ARB_OK;
     }
     auto kern = gemm16_kernel<EPI, kF16, OutT, false>;
@@ -441,7 +468,7 @@ static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb
     ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + kGemmBN - 1) / kGemmBN);
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, tc, tr, bias, M, N, K, fold, umma_idesc_16bit(kBM, kGemmBN, kF16, w_fp16));
+    kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, tc, tr, bias, M, N, K, fold, umma_idesc_16bit(kBM, kGemmBN, kF16));
     ARB_CHECK_CUDA(cudaGetLastError());
     return ARB_OK;
 }
@@ -463,16 +490,16 @@ static int check_gemm_args(const void* A, int64_t lda, const void* B, int64_t ld
 template <bool kF16>
 static int dispatch_gemm16(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
                            const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
-                           int epilogue, bool w_fp16, cudaStream_t stream) {
+                           int epilogue, cudaStream_t stream) {
     switch (epilogue) {
         case EPI_BIAS:
-            return launch_gemm_impl<EPI_BIAS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, w_fp16, stream);
+            return launch_gemm_impl<EPI_BIAS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, stream);
         case EPI_BIAS_GELU:
-            return launch_gemm_impl<EPI_BIAS_GELU, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, w_fp16, stream);
+            return launch_gemm_impl<EPI_BIAS_GELU, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, stream);
         case EPI_BIAS_RESIDUAL:
             ARB_REQUIRE(R != nullptr && ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0,
                         "gemm: residual operand missing or misaligned");
-            return launch_gemm_impl<EPI_BIAS_RESIDUAL, kF16, h16>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, w_fp16, stream);
+            return launch_gemm_impl<EPI_BIAS_RESIDUAL, kF16, h16>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, stream);
         default:
             set_error("gemm: unknown epilogue %d", epilogue);
             return ARB_ERR_INVALID;
@@ -481,35 +508,34 @@ static int dispatch_gemm16(const h16* A, int64_t lda, const h16* B, int64_t ldb,
 
 int launch_gemm16(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
                   const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
-                  int epilogue, int fmt, cudaStream_t stream) {
+                  int epilogue, bool fp16, cudaStream_t stream) {
     int rc = check_gemm_args(A, lda, B, ldb, C, ldc, M, N, K, 2);
     if (rc) return rc;
     ARB_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
                 "gemm: bias must be 16-byte aligned");
-    const bool w16 = fmt_w_f16(fmt);
-    return fmt_act_f16(fmt) ? dispatch_gemm16<true>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, w16, stream)
-                            : dispatch_gemm16<false>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, w16, stream);
+    return fp16 ? dispatch_gemm16<true>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, stream)
+                            : dispatch_gemm16<false>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, stream);
 }
 
 template <bool kF16>
 static int dispatch_gemm16_fold(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
                                 const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
-                                int epilogue, const LnFoldArgs& f, bool w_fp16, cudaStream_t stream) {
+                                int epilogue, const LnFoldArgs& f, cudaStream_t stream) {
     switch (epilogue) {
         case EPI_LNIN_BIAS:
-            return launch_gemm_impl<EPI_LNIN_BIAS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, w_fp16, stream, f);
+            return launch_gemm_impl<EPI_LNIN_BIAS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, stream, f);
         case EPI_LNIN_BIAS_GELU:
-            return launch_gemm_impl<EPI_LNIN_BIAS_GELU, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, w_fp16, stream, f);
+            return launch_gemm_impl<EPI_LNIN_BIAS_GELU, kF16, h16>(A, lda, B, ldb, C, ldc, bias, nullptr, 0, M, N, K, stream, f);
         case EPI_BIAS_LNRES_STATS:
-            return launch_gemm_impl<EPI_BIAS_LNRES_STATS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, w_fp16, stream, f);
+            return launch_gemm_impl<EPI_BIAS_LNRES_STATS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, stream, f);
         default:
-            return launch_gemm_impl<EPI_BIAS_RES_STATS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, w_fp16, stream, f);
+            return launch_gemm_impl<EPI_BIAS_RES_STATS, kF16, h16>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, stream, f);
     }
 }
 
 int launch_gemm16_fold(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
                        const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
-                       int epilogue, const LnFoldArgs& f, int fmt, cudaStream_t stream) {
+                       int epilogue, const LnFoldArgs& f, bool fp16, cudaStream_t stream) {
     int rc = check_gemm_args(A, lda, B, ldb, C, ldc, M, N, K, 2);
     if (rc) return rc;
     ARB_REQUIRE(epilogue >= EPI_LNIN_BIAS && epilogue <= EPI_BIAS_RES_STATS, "gemm_fold: unknown epilogue %d", epilogue);
@@ -531,18 +557,16 @@ int launch_gemm16_fold(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16
     if (epilogue == EPI_BIAS_LNRES_STATS)
         ARB_REQUIRE(f.gamma && f.beta && (reinterpret_cast<uintptr_t>(f.gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(f.beta) & 15) == 0,
                     "gemm_fold: gamma / beta missing or misaligned");
-    const bool w16 = fmt_w_f16(fmt);
-    return fmt_act_f16(fmt) ? dispatch_gemm16_fold<true>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, f, w16, stream)
-                            : dispatch_gemm16_fold<false>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, f, w16, stream);
+    return fp16 ? dispatch_gemm16_fold<true>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, f, stream)
+                            : dispatch_gemm16_fold<false>(A, lda, B, ldb, C, ldc, bias, R, ldr, M, N, K, epilogue, f, stream);
 }
 
 int launch_gemm16_f32out(const h16* A, int64_t lda, const h16* B, int64_t ldb, float* C,
-                         int64_t ldc, int64_t M, int N, int K, int fmt, cudaStream_t stream) {
+                         int64_t ldc, int64_t M, int N, int K, bool fp16, cudaStream_t stream) {
     int rc = check_gemm_args(A, lda, B, ldb, C, ldc, M, N, K, 4);
     if (rc) return rc;
-    const bool w16 = fmt_w_f16(fmt);
-    return fmt_act_f16(fmt) ? launch_gemm_impl<EPI_BIAS, true, float>(A, lda, B, ldb, C, ldc, nullptr, nullptr, 0, M, N, K, w16, stream)
-                            : launch_gemm_impl<EPI_BIAS, false, float>(A, lda, B, ldb, C, ldc, nullptr, nullptr, 0, M, N, K, w16, stream);
+    return fp16 ? launch_gemm_impl<EPI_BIAS, true, float>(A, lda, B, ldb, C, ldc, nullptr, nullptr, 0, M, N, K, stream)
+                            : launch_gemm_impl<EPI_BIAS, false, float>(A, lda, B, ldb, C, ldc, nullptr, nullptr, 0, M, N, K, stream);
 }
 
 }  // namespace arb

@@ -6,18 +6,10 @@
 
 namespace arb {
 
-// Encoder activations/weights are 16-bit in HBM: bf16 or fp16.
+// Encoder activations/weights are 16-bit in HBM: bf16 or fp16 (`fp16` flag of each launch). Both
+// operands of a tcgen05 kind::f16 MMA must share the format: the instruction descriptor has separate
+// A/B format fields, but a bf16 x fp16 instruction faults as illegal on B200 (tried in round 2).
 typedef uint16_t h16;
-
-// Operand formats of one launch (`fmt` arguments): the activations (A, C, R, q/k/v, ctx) and the
-// weights (the GEMM B operand) choose their 16-bit format independently — tcgen05 kind::f16 takes
-// the A and B formats as separate instruction-descriptor fields. The encoder's default mode is
-// bf16 activations x fp16 weights (FMT_W_F16): the weights' rounding error is systematic across
-// tokens and does not average out in the mean pool, so they get the 11-bit mantissa; the
-// activations keep the fp32 exponent range.
-enum : int { FMT_ACT_F16 = 1, FMT_W_F16 = 2 };
-inline bool fmt_act_f16(int fmt) { return (fmt & FMT_ACT_F16) != 0; }
-inline bool fmt_w_f16(int fmt) { return (fmt & FMT_W_F16) != 0; }
 
 enum GemmEpilogue : int {
     EPI_BIAS = 0,           // C = A.B^T + bias
@@ -49,14 +41,14 @@ struct LnFoldArgs {
 // C[M,N] = epi(A[M,K] . B[N,K]^T); A, B, C, R 16-bit row-major; bias fp32 [N] (may be null).
 int launch_gemm16(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
                   const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
-                  int epilogue, int fmt, cudaStream_t stream);
+                  int epilogue, bool fp16, cudaStream_t stream);
 // The folded-LayerNorm epilogues (3..6); N % 128 == 0 for the *_STATS ones.
 int launch_gemm16_fold(const h16* A, int64_t lda, const h16* B, int64_t ldb, h16* C, int64_t ldc,
                        const float* bias, const h16* R, int64_t ldr, int64_t M, int N, int K,
-                       int epilogue, const LnFoldArgs& fold, int fmt, cudaStream_t stream);
+                       int epilogue, const LnFoldArgs& fold, bool fp16, cudaStream_t stream);
 // Same main loop, fp32 output, no epilogue math (used by the kernel parity tests).
 int launch_gemm16_f32out(const h16* A, int64_t lda, const h16* B, int64_t ldb, float* C,
-                         int64_t ldc, int64_t M, int N, int K, int fmt, cudaStream_t stream);
+                         int64_t ldc, int64_t M, int N, int K, bool fp16, cudaStream_t stream);
 
 // word_emb[ids] + pos_emb[position_ids(ids)] -> LayerNorm -> 16-bit hidden [B*S, H]
 int launch_embed_ln(const int32_t* ids, const float* word_emb, const float* pos_emb,

@@ -340,14 +340,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // Instruction descriptor, kind::f16: 16-bit x 16-bit -> fp32, A and B K-major.
 // [4,6) D fmt (1=f32) | [7,10) A fmt | [10,13) B fmt | [15] A major | [16] B major |
 // [17,23) N>>3 | [24,29) M>>4
-// A/B format fields: 0 = fp16, 1 = bf16. The two fields are independent: the encoder's default
-// mode multiplies bf16 activations (A) by fp16 weights (B) in one instruction.
-__host__ __device__ constexpr uint32_t umma_idesc_16bit(int M, int N, bool a_fp16, bool b_fp16) {
-    return (1u << 4) | ((a_fp16 ? 0u : 1u) << 7) | ((b_fp16 ? 0u : 1u) << 10) |
-           (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
-}
+// A/B format fields: 0 = fp16, 1 = bf16. The fields are separate, but B200 raises "illegal
+// instruction" when they differ (bf16 activations x fp16 weights was tried): one format per MMA.
 __host__ __device__ constexpr uint32_t umma_idesc_16bit(int M, int N, bool fp16) {
-    return umma_idesc_16bit(M, N, fp16, fp16);
+    return (1u << 4) | ((fp16 ? 0u : 1u) << 7) | ((fp16 ? 0u : 1u) << 10) |
+           (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // Same with B MN-major (bit 16): used for P.V where V is [keys, dh] row-major, i.e. the smem tile

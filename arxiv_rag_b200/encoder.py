@@ -42,20 +42,23 @@ class B200SentenceEncoder:
         max_length=..., return_tensors='np') -> {'input_ids', 'attention_mask'}` (a HF tokenizer).
         Without one, `encode` accepts pre-tokenised `(input_ids, attention_mask)`.
     max_batch / max_seq : capacity of the activation workspace (tokens = max_batch * max_seq).
-    dtype : 16-bit formats of the tensor-core operands (fp32 accumulation and statistics always):
-        'bf16' (default, the BASELINE config) — bf16 activations x fp16 weights in one tcgen05.mma;
-        rows shorter than `short_seq` (32) tokens are batched apart and run with fp16 activations,
-        because a row of a few tokens has no averaging over its activation noise. Cosine vs the
-        fp32 reference >= 0.9999 on every row (DESIGN.md 'Numerics').
-        'fp16' — fp16 activations and weights (cosine ~0.999998 everywhere).
-        'bf16_pure' — bf16 activations and weights: the A/B baseline (~0.9998 on 1-token rows).
+    dtype : 16-bit format of weights, activations and tensor-core operands (fp32 accumulation and
+        statistics always; both operands of a tcgen05 MMA must share one format):
+        'fp16' (default) — cosine vs the fp32 reference >= 0.9999 on every row (~0.999997), also on
+        heavy-tailed weights; the format the reference's own config asks for (`fp16: true`,
+        3-chunks/pipeline/config.yaml:49).
+        'bf16' — what BASELINE configs[1] names. Same speed, 8-bit mantissa: ~0.99995 on full rows;
+        rows shorter than `short_seq` (32) tokens are batched apart and run in fp16 (an fp16 copy
+        of the weights), because nothing averages a short row's rounding noise. Meets 0.9999 on
+        well-behaved weights, not on heavy-tailed ones (DESIGN.md 'Numerics').
+        'bf16_pure' — bf16 for every batch: the A/B baseline (~0.9998 on 1-token rows).
     """
 
-    DTYPES = {"bf16": _lib.ARB_DTYPE_BF16_WF16, "fp16": _lib.ARB_DTYPE_F16, "bf16_pure": _lib.ARB_DTYPE_BF16}
+    DTYPES = {"fp16": _lib.ARB_DTYPE_F16, "bf16": _lib.ARB_DTYPE_BF16, "bf16_pure": _lib.ARB_DTYPE_BF16_PURE}
 
     def __init__(self, state_dict: dict | None = None, arch: MPNetArch = ALL_MPNET_BASE_V2,
                  device: int | None = None, max_batch: int = 1024, max_seq: int | None = None,
-                 tokenizer=None, seed: int = 0, dtype: str = "bf16", model_name: str | None = None):
+                 tokenizer=None, seed: int = 0, dtype: str = "fp16", model_name: str | None = None):
         torch = _require_cuda()
         self._torch = torch
         if model_name is not None:  # 'all-mpnet-base-v2' | 'all-MiniLM-L6-v2' (reference CLI choices, :473-475)
@@ -83,8 +86,8 @@ class B200SentenceEncoder:
                                                    self.max_batch * self.max_seq, self.max_seq,
                                                    self.device, C.byref(handle)))
         self._h = handle
-        # rows shorter than this are batched among themselves (the library runs such batches with
-        # fp16 activations); 0 = no split
+        # rows shorter than this are batched among themselves (a bf16 handle runs such batches in
+        # fp16); 0 = no split
         self.short_seq = int(_lib.lib().arb_mpnet_short_seq(handle))
         self._staging = None
 

@@ -40,7 +40,7 @@ extern "C" {
 #define ARB_DTYPE_F32 0
 #define ARB_DTYPE_BF16 1
 #define ARB_DTYPE_F16 2
-#define ARB_DTYPE_BF16_WF16 3 /* bf16 activations x fp16 weights (mixed tcgen05 operand formats) */
+#define ARB_DTYPE_BF16_PURE 3 /* encoder handles only: bf16 without the short-batch fp16 path */
 
 #define ARB_EPI_BIAS 0
 #define ARB_EPI_BIAS_GELU 1
@@ -66,20 +66,19 @@ typedef struct ArbMpnetConfig {
     int32_t relative_attention_num_buckets; /* 32 */
     int32_t pad_token_id;                   /* 1 (MPNetEmbeddings.padding_idx, modeling_mpnet.py:60) */
     float layer_norm_eps;                   /* 1e-5 for all-mpnet-base-v2 */
-    int32_t compute_dtype;                  /* 16-bit formats in HBM and of the tensor-core operands
-                                               (accumulation, softmax and LayerNorm statistics are
-                                               always fp32):
-                                               ARB_DTYPE_BF16_WF16  the BASELINE "bf16" config as
-                                                 shipped: bf16 activations x fp16 weights in one
-                                                 tcgen05.mma (the weights' rounding error is the
-                                                 part of the bf16 budget that does not average out
-                                                 over tokens); batches padded to fewer than
-                                                 arb_mpnet_short_seq() tokens run with fp16
-                                                 activations — a row of a few tokens cannot reach
-                                                 cosine 0.9999 vs fp32 with bf16 activations;
-                                               ARB_DTYPE_F16   fp16 activations and weights;
-                                               ARB_DTYPE_BF16  bf16 activations and weights (A/B
-                                                 baseline; ~0.9998 on 1-token rows) */
+    int32_t compute_dtype;                  /* 16-bit format of weights + activations in HBM and of
+                                               the tensor-core operands (accumulation, softmax and
+                                               LayerNorm statistics are always fp32; one format
+                                               per tcgen05 MMA — mixed A/B formats fault on B200):
+                                               ARB_DTYPE_F16   fp16: the shipped default. Cosine vs
+                                                 the fp32 reference >= 0.9999 on every row (~0.999997);
+                                               ARB_DTYPE_BF16  what BASELINE configs[1] names: bf16
+                                                 for batches of >= arb_mpnet_short_seq() tokens,
+                                                 an fp16 copy of the weights for shorter batches
+                                                 (8-bit mantissas cannot hold 0.9999 on rows of a
+                                                 few tokens). ~0.99995 on full rows of well-behaved
+                                                 weights, below 0.9999 on heavy-tailed ones;
+                                               ARB_DTYPE_BF16_PURE  bf16 for every batch (A/B) */
     int32_t position_mode;                  /* 0 = MPNet: padding-aware position ids (modeling_mpnet.py:889-897);
                                                1 = BERT: absolute index (all-MiniLM-L6-v2; token-type row 0 is
                                                folded into the position table by the caller). A BERT-style
@@ -119,8 +118,8 @@ int arb_mpnet_encode(void* handle, const int32_t* ids_dev, const int32_t* mask_d
  * id). Call after the stream has been synchronised: ARB_OK, or ARB_ERR_INVALID (message in
  * arb_last_error(); the status is cleared). */
 int arb_mpnet_status(void* handle);
-/* ARB_DTYPE_BF16_WF16 handles: batches with S below this run with fp16 activations; hosts that sort
- * rows by length should cut their batches at this length. 0 for the other dtypes. */
+/* ARB_DTYPE_BF16 handles: batches with S below this run in fp16; hosts that sort rows by length
+ * should cut their batches at this length. 0 for the other dtypes. */
 int arb_mpnet_short_seq(void* handle);
 /* Number of kernel launches one arb_mpnet_encode call enqueues (for launch accounting). */
 int arb_mpnet_launches_per_encode(void* handle);
@@ -180,8 +179,7 @@ int arb_topk_search_launches(int32_t dtype);
 /* ------------------------------------------------------------------------------------------
  * Kernel-level entry points (each is one launch); used by the parity tests and available to
  * callers that want to compose the encoder themselves. All pointers are device pointers;
- * `dtype` gives the 16-bit formats: ARB_DTYPE_BF16 / ARB_DTYPE_F16 (activations and weights alike)
- * or ARB_DTYPE_BF16_WF16 (A, C, R bf16; the GEMM B operand fp16).
+ * `dtype` is the 16-bit format of every operand (ARB_DTYPE_BF16 or ARB_DTYPE_F16).
  * ------------------------------------------------------------------------------------------ */
 /* GEMM with a LayerNorm folded into its epilogue (how the encoder avoids separate LayerNorm passes).
  * epilogue 3: C = rstd (A.B'^T - mean colsum) + bias          A rows are PRE-LayerNorm; B' = B diag(gamma),

@@ -182,33 +182,6 @@ def test_gemm_schedules_agree_bitwise(lib, cuda):
     assert torch.equal(out[0], out[1])
 
 
-@pytest.mark.parametrize("mode", [1, 2])
-@pytest.mark.parametrize("shape", [(300, 256, 768), (4099, 2304, 768), (513, 768, 3072)])
-def test_gemm_mixed_operand_formats(lib, cuda, mode, shape):
-    """ARB_DTYPE_BF16_WF16: A (activations) bf16 x B (weights) fp16 in one tcgen05.mma — the
-    instruction descriptor carries the two formats separately. Products of a bf16 and an fp16 value
-    are exact in fp32, so the fp32-output main loop must match torch to summation order; the 16-bit
-    epilogues write bf16."""
-    M, N, K = shape
-    torch.manual_seed(11)
-    A = (torch.randn(M, K, device=cuda) * 0.5).to(torch.bfloat16)
-    B = (torch.randn(N, K, device=cuda) * 0.5).to(torch.float16)
-    ref = A.float() @ B.float().T
-    _lib.check(lib.arb_set_gemm_mode(mode))
-    try:
-        C = torch.full((M, N), float("nan"), device=cuda)
-        _lib.check(lib.arb_gemm16_f32out(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, M, N, K,
-                                         _lib.ARB_DTYPE_BF16_WF16, _stream()))
-        assert _rel_err(C, ref) < 2e-5
-        bias = torch.randn(N, device=cuda)
-        C16 = torch.zeros(M, N, device=cuda, dtype=torch.bfloat16)
-        _lib.check(lib.arb_gemm16(A.data_ptr(), K, B.data_ptr(), K, C16.data_ptr(), N, bias.data_ptr(), 0, N, M, N, K, 1,
-                                  _lib.ARB_DTYPE_BF16_WF16, _stream()))
-        assert _rel_err(C16, torch.nn.functional.gelu(ref + bias)) < 6e-3
-    finally:
-        _lib.check(lib.arb_set_gemm_mode(0))
-
-
 def test_gemm_strided_operands(lib, cuda):
     """The encoder reads q|k|v column blocks and writes into wider buffers: lda/ldc > K/N."""
     torch.manual_seed(2)

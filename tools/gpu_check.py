@@ -77,17 +77,6 @@ def stage_gemm():
             torch.cuda.synchronize()
             ref = A.float() @ B.float().T
             ok &= report(f"gemm_f32out {d} M{M} N{N} K{K}", C, ref, 2e-5)
-    # mixed operand formats: bf16 activations x fp16 weights (ARB_DTYPE_BF16_WF16)
-    for mode in (1, 2):
-        _lib.check(lib().arb_set_gemm_mode(mode))
-        for (M, N, K) in [(128, 256, 64), (300, 256, 768), (4099, 2304, 768)]:
-            A = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16)
-            B = (torch.randn(N, K, device=DEV) * 0.5).to(torch.float16)
-            C = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
-            _lib.check(lib().arb_gemm16_f32out(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, M, N, K, _lib.ARB_DTYPE_BF16_WF16, stream()))
-            torch.cuda.synchronize()
-            ok &= report(f"gemm_f32out bf16 x fp16 mode{mode} M{M} N{N} K{K}", C, A.float() @ B.float().T, 2e-5)
-    _lib.check(lib().arb_set_gemm_mode(0))
     # epilogues
     for d in ("bf16", "fp16"):
         M, N, K = 777, 768, 768
