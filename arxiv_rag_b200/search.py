@@ -63,15 +63,25 @@ class CorpusIndex:
         self.dtype_code = _lib.ARB_DTYPE_F32 if self.corpus.dtype == torch.float32 else _lib.ARB_DTYPE_BF16
         self._ws = None
 
+    def workspace_bytes(self, Q: int, k: int) -> int:
+        return int(_lib.lib().arb_topk_search_workspace_bytes(self.dtype_code, Q, self.n, self.d, k))
+
+    def new_workspace(self, Q: int, k: int):
+        """A workspace tensor of its own for one (Q, k) — what a captured CUDA graph must use: the
+        shared eager workspace below is replaced when a later call needs more bytes, and a graph
+        that kept its address would then write into freed memory."""
+        return self._torch.empty(max(self.workspace_bytes(Q, k), 256), dtype=self._torch.uint8, device=self.corpus.device)
+
     def _workspace(self, Q: int, k: int):
-        need = int(_lib.lib().arb_topk_search_workspace_bytes(self.dtype_code, Q, self.n, self.d, k))
+        need = self.workspace_bytes(Q, k)
         if self._ws is None or self._ws.numel() < need:
             self._ws = self._torch.empty(max(need, 256), dtype=self._torch.uint8, device=self.corpus.device)
         return self._ws, need
 
-    def search(self, queries, k: int = 10, out_scores=None, out_ids=None):
+    def search(self, queries, k: int = 10, out_scores=None, out_ids=None, workspace=None):
         """queries `[Q, D]` (same dtype family as the corpus; converted if not) ->
-        (scores float32 `[Q,k]`, ids int64 `[Q,k]`) as CUDA tensors, enqueued on the current stream."""
+        (scores float32 `[Q,k]`, ids int64 `[Q,k]`) as CUDA tensors, enqueued on the current stream.
+        `workspace`: a tensor from `new_workspace(Q, k)` to use instead of the shared one."""
         torch = self._torch
         if isinstance(queries, np.ndarray):
             queries = torch.from_numpy(np.ascontiguousarray(queries))
@@ -89,7 +99,12 @@ class CorpusIndex:
             out_scores.fill_(float("-inf"))
             out_ids.fill_(-1)
             return out_scores, out_ids
-        ws, need = self._workspace(Q, k)
+        if workspace is not None:
+            ws = workspace
+            if ws.numel() < self.workspace_bytes(Q, k):
+                raise ValueError("workspace too small for this (Q, k)")
+        else:
+            ws, _ = self._workspace(Q, k)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().arb_topk_search(_lib.ptr(q), _lib.ptr(self.corpus), self.dtype_code, Q,
                                                   self.n, self.d, k, _lib.ptr(out_scores), _lib.ptr(out_ids),
@@ -220,26 +235,29 @@ class ShardedCorpusIndex:
     def exchange(self) -> str:
         return "peer-memory kernel (CUDA IPC over NVLink)" if self._exch is not None else "nccl all_gather"
 
-    def _buffers(self, Q: int, k: int):
+    def _new_buffers(self, Q: int, k: int):
         torch = self.index._torch
+        dev = self.index.corpus.device
+        rec = int(_lib.lib().arb_topk_record_bytes(Q, k))
+        return (torch.empty(rec, dtype=torch.uint8, device=dev),
+                torch.empty(self.world * rec, dtype=torch.uint8, device=dev),
+                torch.empty((Q, k), dtype=torch.float32, device=dev),
+                torch.empty((Q, k), dtype=torch.int64, device=dev))
+
+    def _buffers(self, Q: int, k: int):
         key = (Q, k)
         if key not in self._bufs:
-            dev = self.index.corpus.device
-            rec = int(_lib.lib().arb_topk_record_bytes(Q, k))
-            self._bufs[key] = (torch.empty(rec, dtype=torch.uint8, device=dev),
-                               torch.empty(self.world * rec, dtype=torch.uint8, device=dev),
-                               torch.empty((Q, k), dtype=torch.float32, device=dev),
-                               torch.empty((Q, k), dtype=torch.int64, device=dev))
+            self._bufs[key] = self._new_buffers(Q, k)
         return self._bufs[key]
 
-    def _search_into(self, queries, k: int, bufs):
+    def _search_into(self, queries, k: int, bufs, workspace=None):
         torch = self.index._torch
         local, gathered, out_s, out_i = bufs
         Q = queries.shape[0]
         ids_off = int(_lib.lib().arb_topk_record_ids_offset(Q, k))
         ls = local[:Q * k * 4].view(torch.float32).view(Q, k)
         li = local[ids_off:ids_off + Q * k * 8].view(torch.int64).view(Q, k)
-        self.index.search(queries, k, out_scores=ls, out_ids=li)
+        self.index.search(queries, k, out_scores=ls, out_ids=li, workspace=workspace)
         if self._exch is not None and local.numel() <= self.peer_slot_bytes:
             with torch.cuda.device(local.device):
                 _lib.check(_lib.lib().arb_topk_exchange_merge(_lib.ptr(local), _lib.ptr(self._exch[2]), self.rank, self.world,
@@ -272,15 +290,17 @@ class ShardedCorpusIndex:
         if key not in self._graphs:
             static_q = torch.empty_like(queries, dtype=self.index.corpus.dtype, device=self.index.corpus.device)
             static_q.copy_(queries)
-            self.index._workspace(Q, k)  # allocate outside the capture
-            bufs = self._buffers(Q, k) if self.world > 1 else None
+            # every captured graph owns its workspace and result buffers: the eager path's shared
+            # workspace may be reallocated by a later, larger call while this graph is still replayed
+            ws = self.index.new_workspace(Q, k)
+            bufs = self._new_buffers(Q, k) if self.world > 1 else None
             outs = None if self.world > 1 else (torch.empty((Q, k), dtype=torch.float32, device=static_q.device),
                                                 torch.empty((Q, k), dtype=torch.int64, device=static_q.device))
 
             def run():
                 if self.world > 1:
-                    return self._search_into(static_q, k, bufs)
-                return self.index.search(static_q, k, out_scores=outs[0], out_ids=outs[1])
+                    return self._search_into(static_q, k, bufs, workspace=ws)
+                return self.index.search(static_q, k, out_scores=outs[0], out_ids=outs[1], workspace=ws)
 
             side = torch.cuda.Stream(device=static_q.device)
             side.wait_stream(torch.cuda.current_stream())
@@ -290,8 +310,8 @@ class ShardedCorpusIndex:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 res = run()
-            self._graphs[key] = (g, static_q, res)
-        g, static_q, res = self._graphs[key]
+            self._graphs[key] = (g, static_q, res, ws, bufs)  # ws / bufs: kept alive for the graph
+        g, static_q, res = self._graphs[key][:3]
         static_q.copy_(queries, non_blocking=True)
         g.replay()
         return res

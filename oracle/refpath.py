@@ -10,8 +10,10 @@ Follows 4-embed/generation/generate_embeddings_parallel.py:
   * `generate_embeddings_worker` — :131-177 (sub-batch loop, `.encode` flags of :146-153).
   * `generate_embeddings_parallel` — :179-269 with the mis-indented `for` at :239 re-indented;
     task split :197-200, unordered collect :213-226, reorder by batch_idx :236-244,
-    count fix-up :259-267. The process pool is replaced by an in-process loop or a
-    torch-thread-parallel model (the arithmetic and ordering are what is being restated).
+    count fix-up :259-267. Tasks run in-process (one model, all torch threads);
+  * `generate_embeddings_pool` — the same with the reference's own process pool: `Pool(num_workers,
+    initializer=init_worker_model)` (:205), `num_workers` = 75 % of the cores (:190), `spawn` start
+    (:614), one model per process (:40-65), unordered collect + reorder.
 Input is pre-tokenised (ids, mask): no tokenizer vocabulary exists offline.
 """
 from __future__ import annotations
@@ -91,3 +93,59 @@ def generate_embeddings_parallel(ids: np.ndarray, mask: np.ndarray, model, model
         else:
             embeddings = embeddings[:n]
     return embeddings
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's process-pool variant (:190, :205, :213-226, :614)
+# ---------------------------------------------------------------------------------------------
+_pool_model = None
+
+
+def _pool_init(arch, weight_seed: int):
+    """init_worker_model (:40-65): one CPU model per worker process."""
+    global _pool_model
+    from arxiv_rag_b200.weights import synthetic_state_dict
+
+    _pool_model = OracleSentenceTransformer(arch, synthetic_state_dict(arch, weight_seed))
+
+
+def _pool_task(args):
+    return generate_embeddings_worker(args, _pool_model)
+
+
+def default_pool_workers() -> int:
+    """`max(1, int(cpu_count * 0.75))` (:190)."""
+    import os
+
+    return max(1, int((os.cpu_count() or 1) * 0.75))
+
+
+class ReferencePool:
+    """The reference's worker pool, kept open across calls so that a benchmark can time the
+    encode work without the per-run model construction."""
+
+    def __init__(self, arch, weight_seed: int = 0, num_workers: Optional[int] = None):
+        import multiprocessing as mp
+
+        self.num_workers = num_workers or default_pool_workers()
+        self.pool = mp.get_context("spawn").Pool(self.num_workers, initializer=_pool_init, initargs=(arch, weight_seed))
+
+    def generate_embeddings_parallel(self, ids: np.ndarray, mask: np.ndarray, model_name: str = "all-mpnet-base-v2",
+                                     batch_size: int = 200, chunks_per_worker: int = 500) -> List[np.ndarray]:
+        n = ids.shape[0]
+        tasks = []
+        for i in range(0, n, chunks_per_worker):
+            tasks.append(((ids[i:i + chunks_per_worker], mask[i:i + chunks_per_worker]), model_name, batch_size, len(tasks)))
+        results: Dict[int, List[np.ndarray]] = {}
+        for batch_idx, rows, err in self.pool.imap_unordered(_pool_task, tasks):  # :213-226
+            if rows:
+                results[batch_idx] = rows
+        out: List[np.ndarray] = []
+        for i in range(len(tasks)):  # :236-244
+            if i in results:
+                out.extend(results[i])
+        return out
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()

@@ -217,3 +217,36 @@ def test_world_size_2_gloo(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
                          capture_output=True, text=True, env=env, timeout=240)
     assert res.returncode == 0 and "GLOO_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_reference_process_pool_restatement_matches_in_process():
+    """oracle/refpath.ReferencePool (the reference's spawn Pool with one model per worker,
+    generate_embeddings_parallel.py:190,205,213-226,614) returns what the in-process restatement
+    returns, in chunk order."""
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from oracle import refpath, encode_oracle as eo\n"
+        "from arxiv_rag_b200.weights import MPNetArch, synthetic_state_dict\n"
+        "if __name__ == '__main__':\n"
+        "    arch = MPNetArch(vocab_size=1000, num_layers=2)\n"
+        "    ids, mask = eo.synthetic_tokens(12, 24, vocab_size=1000, seed=1)\n"
+        "    pool = refpath.ReferencePool(arch, 0, num_workers=3)\n"
+        "    a = pool.generate_embeddings_parallel(ids, mask, batch_size=2, chunks_per_worker=4)\n"
+        "    pool.close()\n"
+        "    b = refpath.generate_embeddings_parallel(ids, mask, refpath.OracleSentenceTransformer(arch, synthetic_state_dict(arch, 0)), batch_size=2, chunks_per_worker=4)\n"
+        "    assert len(a) == len(b) == 12\n"
+        "    print('MAXDIFF', float(np.abs(np.stack(a) - np.stack(b)).max()))\n"
+    )
+    import tempfile
+
+    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
+        f.write(code)
+        path = f.name
+    try:
+        env = dict(os.environ, OMP_NUM_THREADS="2")
+        out = subprocess.run([sys.executable, path], capture_output=True, text=True, timeout=240, env=env)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert float(out.stdout.split("MAXDIFF")[1]) < 1e-6
+    finally:
+        os.unlink(path)

@@ -179,7 +179,7 @@ def test_out_of_range_token_id_raises(cuda, full_model):
     ids, mask = eo.synthetic_tokens(3, 40, seed=3)
     enc.encode((ids, mask))  # clean batch: no error
     bad = ids.copy()
-    bad[1, 5] = arch.vocab_size + 17
+    bad[0, 5] = arch.vocab_size + 17  # row 0 is the full-length row
     with pytest.raises(ArbError, match="outside the vocabulary"):
         enc.encode((bad, mask))
     enc.encode((ids, mask))  # the status is cleared by the raise

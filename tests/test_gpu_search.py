@@ -228,6 +228,16 @@ def test_sharded_index_graph_replay(cuda):
         gs_, gi_ = idx.search_graphed(q, 10)
         assert torch.equal(es, gs_) and torch.equal(ei, gi_)
     assert len(idx._graphs) == 1
+    # A captured graph owns its workspace: an eager call with a much larger batch (which makes the
+    # shared workspace grow and the allocator recycle the old block) must not disturb a later replay.
+    q_small = torch.nn.functional.normalize(torch.randn(16, 768, device=cuda, generator=g), dim=1).to(torch.bfloat16)
+    want_s, want_i = (t.clone() for t in idx.index.search(q_small, 10))
+    q_big = torch.nn.functional.normalize(torch.randn(5000, 768, device=cuda, generator=g), dim=1).to(torch.bfloat16)
+    idx.search(q_big, 100)
+    junk = torch.full((64 << 20,), 0x7F, dtype=torch.uint8, device=cuda)  # reuse freed blocks with garbage
+    gs_, gi_ = idx.search_graphed(q_small, 10)
+    assert torch.equal(want_s, gs_) and torch.equal(want_i, gi_)
+    del junk
     dist.destroy_process_group()
 
 
