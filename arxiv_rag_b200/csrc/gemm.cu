@@ -9,6 +9,8 @@
 // tile in shared memory, and one thread of the group issues a TMA store (coalesced, clipped at
 // the M/N edges). The residual chunk is TMA-loaded into the same staging tile beforehand, so
 // neither R nor C is ever touched with row-strided global accesses.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tmap.cuh"
@@ -40,11 +42,23 @@ struct GemmTileIter {
 // 0 = auto (pairs when there are more 256-row blocks than CTA pairs), 1 = single CTA, 2 = CTA pairs
 static int g_gemm_mode = 0;
 void set_gemm_mode(int mode) { g_gemm_mode = mode; }
+// ARB_GEMM_COLSMEM=0 keeps the 5-stage kernel with per-row global loads for the o-projection (A/B)
+static const bool g_gemm_colsmem = []() {
+    const char* e = getenv("ARB_GEMM_COLSMEM");
+    return !(e && e[0] == '0');
+}();
 
 // CTA-pair variant: 256 x 256 tiles, 32 KB per stage and CTA (A 128 x 64 + half of B): 5 stages
 // leave room for double-buffered epilogue staging.
 constexpr int kGemm2Stages = 5;
 using Gemm2Smem = PipeSmem<kGemmBN, kGemm2Stages, 4 * kStageTileBytes, 2>;  // two staging tiles per group
+// Pair variant for the LayerNorm(residual) epilogue of a short-K GEMM (the o-projection, K = 768):
+// its tile main loop is only ~6 k cycles, so the epilogue has no slack. One ring stage is given up
+// for 8 KB that hold gamma and (bias + beta) of every output column for the whole kernel
+// (N <= kColSmemMaxN), read back with broadcast shared-memory loads instead of per-row global loads.
+constexpr int kColSmemMaxN = 1024;
+constexpr int kColSmemBytes = 2 * kColSmemMaxN * 4;
+using Gemm2ColSmem = PipeSmem<kGemmBN, kGemm2Stages - 1, 4 * kStageTileBytes + kColSmemBytes, 2>;
 template <bool k2Cta>
 constexpr int kGemmStageBufs = k2Cta ? 2 : 1;
 
@@ -118,7 +132,20 @@ __device__ __forceinline__ float gelu_sigmoid_fit3(float x) {
     return x * r;
 }
 
-// GELU of the fp16 mode: 0 = erf form, 1 = sigmoid fit, 2 = the bf16 mode's tanh fit (build-time A/B)
+// Same fit of u(x), finished with the hardware tanh: gelu = 0.5 x (1 + tanh u). 8 instructions, 1 MUFU;
+// on top of the fit's 2.6e-5 comes MUFU.TANH's 2^-11 relative error, i.e. about half an fp16 ulp of
+// the result.
+__device__ __forceinline__ float gelu_tanh_fit3(float x) {
+    const float x2 = fminf(x * x, 50.0f);
+    const float u = x * fmaf(x2, fmaf(x2, -0.000351518939f, 0.03700566f), 0.797507868f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+    const float h = 0.5f * x;
+    return fmaf(h, t, h);
+}
+
+// GELU of the fp16 mode: 0 = erf form, 1 = sigmoid fit, 2 = the bf16 mode's tanh fit, 3 = tanh with the
+// 3-term fit (build-time A/B)
 #ifndef ARB_GELU_F16
 #define ARB_GELU_F16 0
 #endif
@@ -127,14 +154,16 @@ __device__ __forceinline__ float gelu_f16_mode(float x) {
     return gelu_erf(x);
 #elif ARB_GELU_F16 == 1
     return gelu_sigmoid_fit3(x);
-#else
+#elif ARB_GELU_F16 == 2
     return gelu_tanh_fit(x);
+#else
+    return gelu_tanh_fit3(x);
 #endif
 }
 
 // OutT = h16 (16-bit activations in the kF16 format) or float. k2Cta: launched as clusters of two
 // CTAs that share one 256 x 256 tile through tcgen05 cta_group::2 (see umma_pipe.cuh).
-template <int EPI, bool kF16, typename OutT, bool k2Cta>
+template <int EPI, bool kF16, typename OutT, bool k2Cta, bool kColSmem = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
@@ -147,7 +176,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     constexpr bool kRes = EPI == EPI_BIAS_RESIDUAL || EPI == EPI_BIAS_LNRES_STATS || EPI == EPI_BIAS_RES_STATS;
     constexpr bool kLnRes = EPI == EPI_BIAS_LNRES_STATS;
     constexpr bool kStats = EPI == EPI_BIAS_LNRES_STATS || EPI == EPI_BIAS_RES_STATS;
-    using SM = typename std::conditional<k2Cta, Gemm2Smem, GemmSmem>::type;
+    static_assert(!kColSmem || (k2Cta && EPI == EPI_BIAS_LNRES_STATS), "resident column vectors: pair kernel, LN(residual) epilogue");
+    using SM = typename std::conditional<kColSmem, Gemm2ColSmem, typename std::conditional<k2Cta, Gemm2Smem, GemmSmem>::type>::type;
     using Iter = typename std::conditional<k2Cta, Gemm2TileIter, GemmTileIter>::type;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // SWIZZLE_128B tiles need a 1024-byte aligned base; align by hand (the launcher adds slack).
@@ -202,6 +232,16 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         if (leader) {
             tma_prefetch_desc(&tmap_c);
             if (kRes) tma_prefetch_desc(&tmap_r);
+        }
+        // kColSmem: gamma and (bias + beta) of all N columns live in shared memory for the whole kernel
+        float* col_gamma = reinterpret_cast<float*>(sm.pre() + 4 * kStageTileBytes);
+        float* col_bb = col_gamma + kColSmemMaxN;
+        if constexpr (kColSmem) {
+            for (int j = threadIdx.x - 64; j < N; j += kEpiThreads) {
+                col_gamma[j] = __ldg(fold.gamma + j);
+                col_bb[j] = __ldg(fold.beta + j) + __ldg(bias + j);
+            }
+            named_bar_sync(3, kEpiThreads);
         }
         // residual prefetch cursor (leader thread, kBufs == 2): walks the same (tile, chunk) sequence
         // one live chunk ahead of the epilogue
@@ -294,9 +334,12 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
                 if (!live) continue;
                 any_live = true;
                 ++kc;
-                float v[CW];
+                // the tile's values as pairs: the fp32 math below is packed (fma.rn.f32x2 & co.), which
+                // halves the FMA-pipe issue slots of the epilogue
+                float2 v2[CW / 2];
 #pragma unroll
-                for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
+                for (int j = 0; j < CW / 2; ++j) v2[j] = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                const float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(nmr, nmr);
                 if constexpr (kLnIn) {
                     // LN(x) W^T + b = rstd (x W'^T) - mean rstd c + b'   (columns are whole 64-wide chunks here)
                     const float4* bp = reinterpret_cast<const float4*>(bias + col0);
@@ -304,28 +347,27 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < CW / 4; ++j) {
                         const float4 b4 = __ldg(bp + j), c4 = __ldg(cp + j);
-                        v[4 * j + 0] = fmaf(rstd, v[4 * j + 0], fmaf(nmr, c4.x, b4.x));
-                        v[4 * j + 1] = fmaf(rstd, v[4 * j + 1], fmaf(nmr, c4.y, b4.y));
-                        v[4 * j + 2] = fmaf(rstd, v[4 * j + 2], fmaf(nmr, c4.z, b4.z));
-                        v[4 * j + 3] = fmaf(rstd, v[4 * j + 3], fmaf(nmr, c4.w, b4.w));
+                        v2[2 * j] = __ffma2_rn(rstd2, v2[2 * j], __ffma2_rn(nmr2, make_float2(c4.x, c4.y), make_float2(b4.x, b4.y)));
+                        v2[2 * j + 1] = __ffma2_rn(rstd2, v2[2 * j + 1], __ffma2_rn(nmr2, make_float2(c4.z, c4.w), make_float2(b4.z, b4.w)));
                     }
-                } else if (bias != nullptr) {
+                } else if (!kLnRes && bias != nullptr) {
                     // columns beyond N read zero bias via the clamp; they are clipped by the store
                     const float4* bp = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
                     for (int j = 0; j < CW / 4; ++j) {
                         if (col0 + 4 * j < N) {
                             const float4 b4 = __ldg(bp + j);
-                            v[4 * j + 0] += b4.x;
-                            v[4 * j + 1] += b4.y;
-                            v[4 * j + 2] += b4.z;
-                            v[4 * j + 3] += b4.w;
+                            v2[2 * j] = __fadd2_rn(v2[2 * j], make_float2(b4.x, b4.y));
+                            v2[2 * j + 1] = __fadd2_rn(v2[2 * j + 1], make_float2(b4.z, b4.w));
                         }
                     }
                 }
                 if (kGelu) {
 #pragma unroll
-                    for (int j = 0; j < CW; ++j) v[j] = kF16 ? gelu_f16_mode(v[j]) : gelu_tanh_fit(v[j]);
+                    for (int j = 0; j < CW / 2; ++j) {
+                        v2[j].x = kF16 ? gelu_f16_mode(v2[j].x) : gelu_tanh_fit(v2[j].x);
+                        v2[j].y = kF16 ? gelu_f16_mode(v2[j].y) : gelu_tanh_fit(v2[j].y);
+                    }
                 }
                 if (kRes) {
                     mbar_wait(res_bar, (res_phase >> buf) & 1u);
@@ -334,25 +376,33 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
                     for (int j = 0; j < 8; ++j) {
                         const uint4 u = *reinterpret_cast<const uint4*>(my_row + ((j ^ sw) << 4));
                         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-                        float gm[8], bt[8];
-                        if constexpr (kLnRes) {  // gamma / beta of the 8 columns of this 16-byte piece
-                            const float4* gp = reinterpret_cast<const float4*>(fold.gamma + col0 + 8 * j);
-                            const float4* bp = reinterpret_cast<const float4*>(fold.beta + col0 + 8 * j);
-                            const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), b0 = __ldg(bp), b1 = __ldg(bp + 1);
-                            gm[0] = g0.x; gm[1] = g0.y; gm[2] = g0.z; gm[3] = g0.w;
-                            gm[4] = g1.x; gm[5] = g1.y; gm[6] = g1.z; gm[7] = g1.w;
-                            bt[0] = b0.x; bt[1] = b0.y; bt[2] = b0.z; bt[3] = b0.w;
-                            bt[4] = b1.x; bt[5] = b1.y; bt[6] = b1.z; bt[7] = b1.w;
-                        }
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float2 f = unpack16x2<kF16>(w[q]);
-                            if constexpr (kLnRes) {  // the residual is LN(R) = rstd (R gamma) + (beta - mean rstd gamma)
-                                f.x = fmaf(rstd, f.x * gm[2 * q], fmaf(nmr, gm[2 * q], bt[2 * q]));
-                                f.y = fmaf(rstd, f.y * gm[2 * q + 1], fmaf(nmr, gm[2 * q + 1], bt[2 * q + 1]));
+                        if constexpr (kLnRes) {
+                            // out = acc + bias + LN(R) = acc + (bias + beta) + gamma (rstd R - mean rstd):
+                            // two packed FMAs and one packed add per pair of columns
+                            float4 g0, g1, b0, b1;  // gamma / (bias + beta) of the 8 columns of this 16-byte piece
+                            if constexpr (kColSmem) {
+                                const float4* gs = reinterpret_cast<const float4*>(col_gamma + col0 + 8 * j);
+                                const float4* bs = reinterpret_cast<const float4*>(col_bb + col0 + 8 * j);
+                                g0 = gs[0]; g1 = gs[1]; b0 = bs[0]; b1 = bs[1];
+                            } else {
+                                const float4* gp = reinterpret_cast<const float4*>(fold.gamma + col0 + 8 * j);
+                                const float4* tp = reinterpret_cast<const float4*>(fold.beta + col0 + 8 * j);
+                                const float4* bp = reinterpret_cast<const float4*>(bias + col0 + 8 * j);
+                                g0 = __ldg(gp); g1 = __ldg(gp + 1);
+                                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), c0 = __ldg(bp), c1 = __ldg(bp + 1);
+                                b0 = make_float4(t0.x + c0.x, t0.y + c0.y, t0.z + c0.z, t0.w + c0.w);
+                                b1 = make_float4(t1.x + c1.x, t1.y + c1.y, t1.z + c1.z, t1.w + c1.w);
                             }
-                            v[8 * j + 2 * q] += f.x;
-                            v[8 * j + 2 * q + 1] += f.y;
+                            const float2 gg[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
+                            const float2 bbv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 t = __ffma2_rn(rstd2, unpack16x2<kF16>(w[q]), nmr2);
+                                v2[4 * j + q] = __ffma2_rn(gg[q], t, __fadd2_rn(v2[4 * j + q], bbv[q]));
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) v2[4 * j + q] = __fadd2_rn(v2[4 * j + q], unpack16x2<kF16>(w[q]));
                         }
                     }
                 } else {
@@ -361,30 +411,34 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
                     named_bar_sync(1 + grp, 128);
                 }
                 if constexpr (sizeof(OutT) == 2) {
+                    float2 osum2 = make_float2(0.f, 0.f), osq2 = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         uint4 u;
-                        u.x = pack16x2<kF16>(v[8 * j + 0], v[8 * j + 1]);
-                        u.y = pack16x2<kF16>(v[8 * j + 2], v[8 * j + 3]);
-                        u.z = pack16x2<kF16>(v[8 * j + 4], v[8 * j + 5]);
-                        u.w = pack16x2<kF16>(v[8 * j + 6], v[8 * j + 7]);
+                        u.x = pack16x2<kF16>(v2[4 * j + 0].x, v2[4 * j + 0].y);
+                        u.y = pack16x2<kF16>(v2[4 * j + 1].x, v2[4 * j + 1].y);
+                        u.z = pack16x2<kF16>(v2[4 * j + 2].x, v2[4 * j + 2].y);
+                        u.w = pack16x2<kF16>(v2[4 * j + 3].x, v2[4 * j + 3].y);
                         *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = u;
                         if constexpr (kStats) {
                             // row statistics from the fp32 values: the 16-bit rounding the consumer sees
                             // is zero-mean noise of 2^-9 relative size, far below the LayerNorm's own eps scale
 #pragma unroll
-                            for (int q = 0; q < 8; q += 2) {
-                                osum += v[8 * j + q] + v[8 * j + q + 1];
-                                osq = fmaf(v[8 * j + q], v[8 * j + q], osq);
-                                osq = fmaf(v[8 * j + q + 1], v[8 * j + q + 1], osq);
+                            for (int q = 0; q < 4; ++q) {
+                                osum2 = __fadd2_rn(osum2, v2[4 * j + q]);
+                                osq2 = __ffma2_rn(v2[4 * j + q], v2[4 * j + q], osq2);
                             }
                         }
+                    }
+                    if constexpr (kStats) {
+                        osum += osum2.x + osum2.y;
+                        osq += osq2.x + osq2.y;
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<float4*>(my_row + ((j ^ sw) << 4)) =
-                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            make_float4(v2[2 * j].x, v2[2 * j].y, v2[2 * j + 1].x, v2[2 * j + 1].y);
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(1 + grp, 128);  // every row of the staging tile is written
@@ -440,9 +494,18 @@ static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb
             set_error("cuTensorMapEncodeTiled failed (B half tile)");
             return ARB_ERR_CUDA;
         }
+        constexpr bool kCanColSmem = EPI == EPI_BIAS_LNRES_STATS && sizeof(OutT) == 2;
+        const bool col_smem = kCanColSmem && N <= kColSmemMaxN && K <= 1024 && g_gemm_colsmem;
         auto kern = gemm16_kernel<EPI, kF16, OutT, true>;
-        constexpr int smem = Gemm2Smem::kExtraOffset + 1024;
-        static_assert(smem <= 232448, "pair GEMM shared memory exceeds 227 KB");
+        int smem = Gemm2Smem::kExtraOffset + 1024;
+        static_assert(Gemm2Smem::kExtraOffset + 1024 <= 232448, "pair GEMM shared memory exceeds 227 KB");
+        if constexpr (kCanColSmem) {
+            static_assert(Gemm2ColSmem::kExtraOffset + 1024 <= 232448, "pair GEMM (column vectors) shared memory exceeds 227 KB");
+            if (col_smem) {
+                kern = gemm16_kernel<EPI, kF16, OutT, true, true>;
+                smem = Gemm2ColSmem::kExtraOffset + 1024;
+            }
+        }
         ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         const int64_t tiles = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kGemmBN - 1) / kGemmBN);
         int64_t nclusters = num_sms() / 2;

@@ -23,9 +23,10 @@ ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--seq", type=int, default=384)
 ap.add_argument("--kernels", action="store_true")
 ap.add_argument("--no-check", action="store_true")
+ap.add_argument("--graph", action="store_true", help="also time the step replayed from one CUDA graph")
 args = ap.parse_args()
 
-tag = f"lib={os.path.basename(os.environ.get('ARB_LIB_PATH', 'default'))} defer={os.environ.get('ARB_ATTN_DEFER', '1')} dtype={args.dtype} B{args.batch} S{args.seq}"
+tag = f"lib={os.path.basename(os.environ.get('ARB_LIB_PATH', 'default'))} dtype={args.dtype} B{args.batch} S{args.seq}"
 sd = synthetic_state_dict(ALL_MPNET_BASE_V2, 0)
 enc = B200SentenceEncoder(sd, max_batch=args.batch, max_seq=args.seq, dtype=args.dtype)
 cos_txt = ""
@@ -49,14 +50,28 @@ for _ in range(8):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 8
-print(f"{tag}: {ms:.2f} ms/step {args.batch / ms * 1e3:.0f} chunks/s{cos_txt}", flush=True)
+graph_txt = ""
+if args.graph:
+    enc.encode_tokens_graphed(ids, m)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(8):
+        enc.encode_tokens_graphed(ids, m)
+    e1.record()
+    torch.cuda.synchronize()
+    graph_txt = f" | one CUDA graph: {e0.elapsed_time(e1) / 8:.2f} ms/step"
+print(f"{tag}: {ms:.2f} ms/step {args.batch / ms * 1e3:.0f} chunks/s{graph_txt}{cos_txt}", flush=True)
 if args.kernels:
     from torch.profiler import ProfilerActivity, profile
 
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        e0.record()
         enc.encode_tokens(ids, m)
+        e1.record()
         torch.cuda.synchronize()
     rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
-    for ev in rows[:12]:
+    ksum = sum(e.device_time_total for e in rows if "arb::" in e.key)
+    print(f"    profiled step: {e0.elapsed_time(e1):.2f} ms between events, {ksum / 1e3:.2f} ms inside kernels", flush=True)
+    for ev in rows[:10]:
         print(f"    {ev.key[:100]:100s} n={ev.count:3d} avg {ev.device_time_total / max(ev.count, 1):9.1f} us total {ev.device_time_total / 1e3:7.2f} ms", flush=True)
 enc.close()
