@@ -147,7 +147,7 @@ __device__ __forceinline__ float gelu_tanh_fit3(float x) {
 // GELU of the fp16 mode: 0 = erf form, 1 = sigmoid fit, 2 = the bf16 mode's tanh fit, 3 = tanh with the
 // 3-term fit (build-time A/B)
 #ifndef ARB_GELU_F16
-#define ARB_GELU_F16 0
+#define ARB_GELU_F16 3  // measured on the 1024 x 384 step: erf 80.2 ms, sigmoid fit 82.3, tanh 2-term 78.7, tanh 3-term 77.8
 #endif
 __device__ __forceinline__ float gelu_f16_mode(float x) {
 #if ARB_GELU_F16 == 0
