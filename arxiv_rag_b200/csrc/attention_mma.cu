@@ -1,3 +1,4 @@
+#include <cstdlib>
 // Fused self-attention, mma.sync version: softmax(q.k^T/sqrt(dh) + rel_bias + mask) . v
 // per (sequence, head), never materialising the [S,S] probability matrix in HBM.
 // Follows MPNetSelfAttention.forward (modeling_mpnet.py:162-177) with the shared relative
@@ -19,6 +20,9 @@
 #include "ptx.cuh"
 
 namespace arb {
+
+// shortest sequence the encoder sends to the tcgen05 attention in auto mode
+constexpr int kAttnTcMinSeq = 64;
 
 constexpr int kAttnThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -295,13 +299,24 @@ int launch_attention_mma(const h16* qkv, const float* rel_bias, int max_rel, con
     return ARB_OK;
 }
 
-// impl: 0 = auto (tcgen05 kernel when the shape allows, else mma.sync), 1 = mma.sync, 2 = tcgen05
+// impl: 0 = auto, 1 = mma.sync, 2 = tcgen05 (round-1 schedule), 3 = tcgen05 sub-block pipelined.
+// auto = impl 3 when the shape allows (head dim 64, 64 <= S <= 384), else mma.sync; ARB_ATTN_IMPL
+// overrides auto for A/B runs.
 int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
                      h16* ctx, int B, int S, int heads, int dh, bool fp16, int impl, cudaStream_t stream) {
-    ARB_REQUIRE(impl >= 0 && impl <= 2, "attention: impl %d must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)", impl);
-    const bool tc = impl == 2 || (impl == 0 && rel_bias != nullptr && attention_tc_supported(S, dh));
-    return tc ? launch_attention_tc(qkv, rel_bias, max_rel, mask, ctx, B, S, heads, dh, fp16, stream)
-              : launch_attention_mma(qkv, rel_bias, max_rel, mask, ctx, B, S, heads, dh, fp16, stream);
+    ARB_REQUIRE(impl >= 0 && impl <= 3, "attention: impl %d must be 0 (auto), 1 (mma.sync), 2 or 3 (tcgen05)", impl);
+    if (impl == 0) {
+        static const int forced = []() {
+            const char* e = getenv("ARB_ATTN_IMPL");
+            return e ? atoi(e) : 0;
+        }();
+        impl = forced >= 1 && forced <= 3 ? forced : 3;
+        if (impl == 3 && !(rel_bias != nullptr && attention_tc2_supported(S, dh) && S >= kAttnTcMinSeq)) impl = 1;
+        if (impl == 2 && !(rel_bias != nullptr && attention_tc_supported(S, dh))) impl = 1;
+    }
+    if (impl == 3) return launch_attention_tc2(qkv, rel_bias, max_rel, mask, ctx, B, S, heads, dh, fp16, stream);
+    if (impl == 2) return launch_attention_tc(qkv, rel_bias, max_rel, mask, ctx, B, S, heads, dh, fp16, stream);
+    return launch_attention_mma(qkv, rel_bias, max_rel, mask, ctx, B, S, heads, dh, fp16, stream);
 }
 
 }  // namespace arb

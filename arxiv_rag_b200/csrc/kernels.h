@@ -69,8 +69,12 @@ int launch_adjacent_cosine(const float* emb, float* out, int64_t n, int D, cudaS
 // (entry r <-> j-i = r-(max_rel-1)), mask int32 [B,S]; ctx [B*S, H].
 int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
                      h16* ctx, int B, int S, int heads, int dh, bool fp16, int impl, cudaStream_t stream);
-// the two implementations behind it: mma.sync flash kernel (any S <= 768) and tcgen05/TMEM kernel
+// the implementations behind it: mma.sync flash kernel (any S <= 768; head dim 32) and the tcgen05/TMEM
+// kernels (attention_tc2.cu: sub-block pipelined, the default; attention_tc.cu: the round-1 schedule)
 int launch_attention_mma(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
+                         h16* ctx, int B, int S, int heads, int dh, bool fp16, cudaStream_t stream);
+bool attention_tc2_supported(int S, int dh);
+int launch_attention_tc2(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
                          h16* ctx, int B, int S, int heads, int dh, bool fp16, cudaStream_t stream);
 bool attention_tc_supported(int S, int dh);
 int launch_attention_tc(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,

@@ -304,10 +304,49 @@ def test_embed_layernorm_bert_positions(lib, cuda):
     assert _rel_err(out, ref) < 8e-4
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+def _attention_reference(qkv, relb, mask, B, S, nH, dh, P):
+    H = nH * dh
+    q, k, v = [t.float().view(B, S, nH, dh).transpose(1, 2) for t in qkv.split(H, dim=1)]
+    idx = torch.arange(S, device=qkv.device)
+    bias = relb[:, idx[None, :] - idx[:, None] + (P - 1)]
+    ext = (1.0 - mask[:, None, None, :].float()) * torch.finfo(torch.float32).min
+    sc = q @ k.transpose(-1, -2) / math.sqrt(dh) + bias[None] + ext
+    return (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * S, H)
+
+
+@pytest.mark.parametrize("impl", [2, 3])
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+def test_attention_wide_bias_and_moving_maximum(lib, cuda, dt, impl):
+    """What a trained relative-position table and peaked attention do to the softmax: biases spread
+    over +-10 (29 log2 units between the most and the least favoured offset — the round-1 kernel's
+    shift is only a bound of the row maximum, which pushed fp16 probabilities into subnormals), and
+    keys whose scores grow along the sequence by far more than the lazy-rescale threshold, so that
+    the sub-block pipelined kernel must take its accumulator-rescale path on most rows."""
+    tdt, code, _ = DT[dt]
+    tol = 1.5e-2 if dt == "bf16" else 3e-3
+    B, S, nH, dh, P = 3, 384, 12, 64, 512
+    H = nH * dh
+    torch.manual_seed(12)
+    qkv = torch.randn(B * S, 3 * H, device=cuda)
+    ramp = torch.linspace(0.2, 3.0, S, device=cuda).repeat(B)[:, None]  # later keys score much higher
+    qkv[:, H:2 * H] *= ramp
+    qkv = qkv.to(tdt)
+    relb = (torch.rand(nH, 2 * P - 1, device=cuda) * 20.0 - 10.0)
+    lens = [384, 300, 97]
+    mask = (torch.arange(S, device=cuda)[None, :] < torch.tensor(lens, device=cuda)[:, None]).int().contiguous()
+    ctx = torch.zeros(B * S, H, device=cuda, dtype=tdt)
+    _lib.check(lib.arb_attention16(qkv.data_ptr(), relb.data_ptr(), P, mask.data_ptr(), ctx.data_ptr(), B, S, nH, dh, code, impl, _stream()))
+    ref = _attention_reference(qkv, relb, mask, B, S, nH, dh, P)
+    live = (torch.arange(S, device=cuda)[None, :] < torch.tensor(lens, device=cuda)[:, None]).reshape(B * S)
+    assert torch.isfinite(ctx.float()).all()
+    assert _rel_err(ctx[live], ref[live]) < tol
+
+
+@pytest.mark.parametrize("impl", [1, 2, 3])
 @pytest.mark.parametrize("dt", ["bf16", "fp16"])
 @pytest.mark.parametrize("case", [(3, 64, [64, 1, 17]), (4, 100, [100, 37, 0, 99]), (2, 384, [384, 200]), (1, 5, [3]),
-                                  (5, 256, [256, 255, 130, 3, 0]), (3, 200, [200, 101, 100])])
+                                  (5, 256, [256, 255, 130, 3, 0]), (3, 200, [200, 101, 100]), (2, 33, [33, 20]),
+                                  (150, 320, [320] * 149 + [11])])
 def test_attention(lib, cuda, dt, case, impl):
     """softmax(qk^T/8 + position_bias + (1-m)*finfo.min) v (modeling_mpnet.py:162-177); S not a
     multiple of the 64-key block, 1-token rows and an all-masked row (uniform attention, as the
