@@ -8,8 +8,9 @@ qkv = torch.randn(B * S, 3 * H, device="cuda").to(torch.bfloat16)
 relb = torch.randn(12, 1023, device="cuda")
 mask = torch.ones(B, S, device="cuda", dtype=torch.int32)
 ctx = torch.empty(B * S, H, device="cuda", dtype=torch.bfloat16)
-for _ in range(2):
-    _lib.check(lib.arb_attention16(qkv.data_ptr(), relb.data_ptr(), 512, mask.data_ptr(), ctx.data_ptr(), B, S, 12, 64,
-                                   _lib.ARB_DTYPE_BF16, 2, torch.cuda.current_stream().cuda_stream))
+for impl in [int(x) for x in os.environ.get("PROF_IMPLS", "2,3").split(",")]:
+    for _ in range(2):
+        _lib.check(lib.arb_attention16(qkv.data_ptr(), relb.data_ptr(), 512, mask.data_ptr(), ctx.data_ptr(), B, S, 12, 64,
+                                       _lib.ARB_DTYPE_BF16, impl, torch.cuda.current_stream().cuda_stream))
 torch.cuda.synchronize()
 print("ok")
