@@ -299,9 +299,9 @@ int launch_attention_mma(const h16* qkv, const float* rel_bias, int max_rel, con
     return ARB_OK;
 }
 
-// impl: 0 = auto, 1 = mma.sync, 2 = tcgen05 (round-1 schedule), 3 = tcgen05 sub-block pipelined.
-// auto = impl 3 when the shape allows (head dim 64, 64 <= S <= 384), else mma.sync; ARB_ATTN_IMPL
-// overrides auto for A/B runs.
+// impl: 0 = auto, 1 = mma.sync, 2 = tcgen05, 3 = tcgen05 with sub-block pipelining (experiment, only in
+// builds with -DARB_WITH_ATTENTION_TC2). auto = impl 2 when the shape allows (head dim 64,
+// 64 <= S <= 384), else mma.sync; ARB_ATTN_IMPL overrides auto for A/B runs.
 int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
                      h16* ctx, int B, int S, int heads, int dh, bool fp16, int impl, cudaStream_t stream) {
     ARB_REQUIRE(impl >= 0 && impl <= 3, "attention: impl %d must be 0 (auto), 1 (mma.sync), 2 or 3 (tcgen05)", impl);
@@ -310,7 +310,7 @@ int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const i
             const char* e = getenv("ARB_ATTN_IMPL");
             return e ? atoi(e) : 0;
         }();
-        impl = forced >= 1 && forced <= 3 ? forced : 3;
+        impl = forced >= 1 && forced <= 3 ? forced : 2;
         if (impl == 3 && !(rel_bias != nullptr && attention_tc2_supported(S, dh) && S >= kAttnTcMinSeq)) impl = 1;
         if (impl == 2 && !(rel_bias != nullptr && attention_tc_supported(S, dh))) impl = 1;
     }

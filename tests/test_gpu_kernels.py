@@ -335,7 +335,10 @@ def test_attention_wide_bias_and_moving_maximum(lib, cuda, dt, impl):
     lens = [384, 300, 97]
     mask = (torch.arange(S, device=cuda)[None, :] < torch.tensor(lens, device=cuda)[:, None]).int().contiguous()
     ctx = torch.zeros(B * S, H, device=cuda, dtype=tdt)
-    _lib.check(lib.arb_attention16(qkv.data_ptr(), relb.data_ptr(), P, mask.data_ptr(), ctx.data_ptr(), B, S, nH, dh, code, impl, _stream()))
+    rc = lib.arb_attention16(qkv.data_ptr(), relb.data_ptr(), P, mask.data_ptr(), ctx.data_ptr(), B, S, nH, dh, code, impl, _stream())
+    if impl == 3 and rc == -4:
+        pytest.skip("attention impl 3 is an experiment compiled only with -DARB_WITH_ATTENTION_TC2")
+    _lib.check(rc)
     ref = _attention_reference(qkv, relb, mask, B, S, nH, dh, P)
     live = (torch.arange(S, device=cuda)[None, :] < torch.tensor(lens, device=cuda)[:, None]).reshape(B * S)
     assert torch.isfinite(ctx.float()).all()
@@ -363,7 +366,10 @@ def test_attention(lib, cuda, dt, case, impl):
     relb = torch.randn(nH, 2 * P - 1, device=cuda) * 0.5
     mask = (torch.arange(S, device=cuda)[None, :] < torch.tensor(lens, device=cuda)[:, None]).int().contiguous()
     ctx = torch.zeros(B * S, H, device=cuda, dtype=tdt)
-    _lib.check(lib.arb_attention16(qkv.data_ptr(), relb.data_ptr(), P, mask.data_ptr(), ctx.data_ptr(), B, S, nH, dh, code, impl, _stream()))
+    rc = lib.arb_attention16(qkv.data_ptr(), relb.data_ptr(), P, mask.data_ptr(), ctx.data_ptr(), B, S, nH, dh, code, impl, _stream())
+    if impl == 3 and rc == -4:
+        pytest.skip("attention impl 3 is an experiment compiled only with -DARB_WITH_ATTENTION_TC2")
+    _lib.check(rc)
     q, k, v = [t.float().view(B, S, nH, dh).transpose(1, 2) for t in qkv.split(H, dim=1)]
     idx = torch.arange(S, device=cuda)
     bias = relb[:, idx[None, :] - idx[:, None] + (P - 1)]

@@ -12,7 +12,7 @@ for (B, S) in [(1024, 384), (1024, 256), (1024, 128), (4096, 64)]:
         ctx = torch.empty(B * S, H, device="cuda", dtype=dt)
         fl = 4.0 * B * 12 * S * S * 64
         line = f"attention B{B} S{S} {str(dt)[6:]}:"
-        for impl in (2, 3):
+        for impl in [int(x) for x in os.environ.get("ATTN_IMPLS", "2").split(",")]:
             call = lambda: _lib.check(lib.arb_attention16(qkv.data_ptr(), relb.data_ptr(), 512, mask.data_ptr(), ctx.data_ptr(), B, S, 12, 64, code, impl, torch.cuda.current_stream().cuda_stream))
             for _ in range(3): call()
             torch.cuda.synchronize()
