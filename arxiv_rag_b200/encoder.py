@@ -39,8 +39,10 @@ class B200SentenceEncoder:
         seeded synthetic weights (`weights.synthetic_state_dict(seed)`), since no checkpoint
         exists offline.
     tokenizer : optional callable `tokenizer(list[str], padding=True, truncation=True,
-        max_length=..., return_tensors='np') -> {'input_ids', 'attention_mask'}` (a HF tokenizer).
-        Without one, `encode` accepts pre-tokenised `(input_ids, attention_mask)`.
+        max_length=..., return_tensors='np') -> {'input_ids', 'attention_mask'}` — a HF tokenizer or
+        the in-tree `tokenizer.WordPieceTokenizer`. `vocab_file=...` builds the in-tree one from the
+        model's `vocab.txt`. Without either, `encode` accepts pre-tokenised `(input_ids, attention_mask)`
+        only (no vocabulary ships offline).
     max_batch / max_seq : capacity of the activation workspace (tokens = max_batch * max_seq).
     dtype : 16-bit format of weights, activations and tensor-core operands (fp32 accumulation and
         statistics always; both operands of a tcgen05 MMA must share one format):
@@ -58,7 +60,8 @@ class B200SentenceEncoder:
 
     def __init__(self, state_dict: dict | None = None, arch: MPNetArch = ALL_MPNET_BASE_V2,
                  device: int | None = None, max_batch: int = 1024, max_seq: int | None = None,
-                 tokenizer=None, seed: int = 0, dtype: str = "fp16", model_name: str | None = None):
+                 tokenizer=None, seed: int = 0, dtype: str = "fp16", model_name: str | None = None,
+                 vocab_file: str | None = None):
         torch = _require_cuda()
         self._torch = torch
         if model_name is not None:  # 'all-mpnet-base-v2' | 'all-MiniLM-L6-v2' (reference CLI choices, :473-475)
@@ -71,8 +74,13 @@ class B200SentenceEncoder:
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.max_seq = int(max_seq or arch.max_seq_length)
         self.max_batch = int(max_batch)
-        self.tokenizer = tokenizer
         self.max_seq_length = min(arch.max_seq_length, self.max_seq)
+        if tokenizer is None and vocab_file is not None:
+            from .tokenizer import WordPieceTokenizer
+
+            tokenizer = WordPieceTokenizer(vocab_file, kind="bert" if arch.kind == "bert" else "mpnet",
+                                           max_length=self.max_seq_length)
+        self.tokenizer = tokenizer
         if state_dict is None:
             state_dict = synthetic_state_dict(arch, seed)
         packed = PackedWeights(arch, state_dict)
@@ -102,7 +110,17 @@ class B200SentenceEncoder:
         module, so rows are unit-norm whether or not `normalize_embeddings` is set."""
         torch = self._torch
         single = isinstance(sentences, str)
-        ids, mask = self._tokenize([sentences] if single else sentences)
+        if single:
+            sentences = [sentences]
+        if self._is_text(sentences):
+            out = self._encode_texts(list(sentences), batch_size)
+            if convert_to_tensor:
+                self.check_status(synchronize=True)
+                return out[0] if single else out
+            res = out.cpu().numpy()
+            self.check_status()
+            return res[0] if single else res
+        ids, mask = self._tokenize(sentences)
         n = ids.shape[0]
         out = torch.empty((n, self.arch.hidden_size), dtype=torch.float32, device=f"cuda:{self.device}")
         if n:
@@ -121,6 +139,55 @@ class B200SentenceEncoder:
         res = out.cpu().numpy()  # synchronises the stream
         self.check_status()
         return res[0] if single else res
+
+    @staticmethod
+    def _is_text(sentences) -> bool:
+        if isinstance(sentences, (dict, tuple)):
+            return False
+        try:
+            return len(sentences) > 0 and isinstance(sentences[0], str)
+        except TypeError:
+            return False
+
+    def _encode_texts(self, sentences: list, batch_size: int):
+        """Strings -> embeddings the way sentence-transformers feeds its model: sort by text length
+        (longest first), cut into batches, tokenise each batch and pad it to its longest row. The
+        tokeniser runs on a background thread two batches ahead of the GPU, and each tokenised batch
+        goes through the two pinned staging buffers, so host work overlaps the forward passes."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        torch = self._torch
+        if self.tokenizer is None:
+            raise RuntimeError(
+                "no tokenizer: the all-mpnet-base-v2 vocabulary is not available offline; pass "
+                "tokenizer=... / vocab_file=... or pre-tokenised (input_ids, attention_mask)")
+        n = len(sentences)
+        out = torch.empty((n, self.arch.hidden_size), dtype=torch.float32, device=f"cuda:{self.device}")
+        order = np.argsort(-np.fromiter((len(t) for t in sentences), dtype=np.int64, count=n), kind="stable")
+        bs = max(1, min(int(batch_size), self.max_batch))
+        groups = [order[i:i + bs] for i in range(0, n, bs)]
+
+        def tokenize(sel):
+            enc = self.tokenizer([sentences[j] for j in sel], padding=True, truncation=True,
+                                 max_length=self.max_seq_length, return_tensors="np")
+            ids = np.asarray(enc["input_ids"]).astype(np.int32, copy=False)
+            mask = np.asarray(enc["attention_mask"]).astype(np.int32, copy=False)
+            return ids[:, :self.max_seq], mask[:, :self.max_seq]
+
+        with ThreadPoolExecutor(max_workers=1) as pool, torch.cuda.device(self.device):
+            ahead = [pool.submit(tokenize, g) for g in groups[:2]]
+            for k, sel in enumerate(groups):
+                ids, mask = ahead.pop(0).result()
+                if k + 2 < len(groups):
+                    ahead.append(pool.submit(tokenize, groups[k + 2]))
+                lengths = mask.sum(axis=1)
+                rows = np.argsort(-lengths, kind="stable")
+                for part in self._batches(rows, lengths, bs):  # a bf16 handle takes its short rows apart
+                    S = max(int(lengths[part].max()), 1)
+                    d_ids, d_mask = self._to_device(ids[part, :S], mask[part, :S])
+                    emb = self.encode_tokens(d_ids, d_mask)
+                    out[torch.from_numpy(sel[part]).to(out.device)] = emb
+        return out
 
     def _batches(self, order: np.ndarray, lengths: np.ndarray, bs: int):
         """Length-sorted rows cut into batches of `bs`; rows shorter than `short_seq` never share a

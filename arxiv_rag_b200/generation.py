@@ -148,9 +148,13 @@ def generate_embeddings_parallel(chunks: List[Dict], model_name: str = "all-mpne
     """Encode `chunks` (dicts with 'text', or with 'input_ids'/'attention_mask' rows) and return one
     float32 row per chunk in input order (reference :179-269).
 
-    Under torch.distributed (one process per GPU) every rank encodes its share of the tasks and
-    the rows are gathered to every rank with `all_gather_object`; single-process runs encode all
-    tasks on the current GPU. `num_workers` is accepted for signature parity: the worker count is
+    Under torch.distributed (one process per GPU) every rank encodes its share of the tasks — no
+    collective on the encode path — and, because this function must return every row like the
+    reference does, the rows are then gathered as ONE fixed-shape float32 tensor per rank
+    (`all_gather_into_tensor` of zero-padded `[max_rows, H]` blocks plus their global row numbers),
+    not as pickled Python lists. Corpus-scale runs should not gather at all: see
+    `generate_embeddings_to_disk`, where every rank writes its own shards. Single-process runs encode
+    all tasks on the current GPU. `num_workers` is accepted for signature parity: the worker count is
     the number of GPUs (world size)."""
     import torch.distributed as dist
 
@@ -182,13 +186,113 @@ def generate_embeddings_parallel(chunks: List[Dict], model_name: str = "all-mpne
             raise RuntimeError(err)
         mine[idx] = rows
     if world > 1:
-        gathered: List[Optional[dict]] = [None] * world
-        dist.all_gather_object(gathered, mine)
-        merged: Dict[int, List[np.ndarray]] = {}
-        for g in gathered:
-            merged.update(g)
-        mine = merged
+        return _gather_rows(mine, tasks, n, dist)
     embeddings = reorder(mine, len(tasks))
     if len(embeddings) != n:
         raise RuntimeError(f"embedding count {len(embeddings)} != chunk count {n}")
     return embeddings
+
+
+def _gather_rows(mine: Dict[int, List[np.ndarray]], tasks, n: int, dist) -> List[np.ndarray]:
+    """All ranks' rows -> the full list in chunk order on every rank, through two fixed-shape
+    collectives (row numbers, rows)."""
+    import torch
+
+    world = dist.get_world_size()
+    starts = {t: s for t, s, _ in tasks}
+    row_ids = [starts[t] + j for t in sorted(mine) for j in range(len(mine[t]))]
+    rows = [r for t in sorted(mine) for r in mine[t]]
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    dim = torch.tensor([rows[0].shape[0] if rows else 0, len(rows)], dtype=torch.int64, device=dev)
+    dist.all_reduce(dim, op=dist.ReduceOp.MAX)
+    H, max_rows = int(dim[0]), int(dim[1])
+    block = torch.zeros((max_rows, H), dtype=torch.float32, device=dev)
+    ids = torch.full((max_rows,), -1, dtype=torch.int64, device=dev)
+    if rows:
+        block[:len(rows)] = torch.from_numpy(np.stack(rows).astype(np.float32, copy=False)).to(dev)
+        ids[:len(rows)] = torch.tensor(row_ids, dtype=torch.int64, device=dev)
+    all_blocks = torch.empty((world * max_rows, H), dtype=torch.float32, device=dev)
+    all_ids = torch.empty((world * max_rows,), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_blocks, block)
+    dist.all_gather_into_tensor(all_ids, ids)
+    valid = all_ids >= 0
+    if int(valid.sum()) != n:
+        raise RuntimeError(f"embedding count {int(valid.sum())} != chunk count {n}")
+    full = torch.empty((n, H), dtype=torch.float32, device=dev)
+    full[all_ids[valid]] = all_blocks[valid]
+    return list(full.cpu().numpy())
+
+
+def generate_embeddings_to_disk(chunks: List[Dict], output_dir: str, model_name: str = "all-mpnet-base-v2",
+                                batch_size: int = 200, shard_rows: int = 10000) -> Dict:
+    """The data-parallel output path for corpus-scale runs: the saved layout of
+    4-embed/utils/save_embeddings_to_disk.py:15-80 (`embeddings_batch_XXXX.npy` float64,
+    `metadata_batch_XXXX.json`, `index.json`), written shard by shard by the rank that encoded it.
+    Shard i holds rows [i*shard_rows, (i+1)*shard_rows); rank r of G takes shards r, r+G, ...; nothing
+    is gathered, ranks only meet at a barrier before rank 0 writes `index.json`. Shards whose files
+    already exist are skipped, so an interrupted run resumes (the reference keeps everything in
+    RAM until the end, :257, :555). Returns the index dict."""
+    import json
+    import os
+    from pathlib import Path
+
+    import torch.distributed as dist
+
+    from .storage import _as_matrix, _meta_row
+
+    out = Path(output_dir)
+    out.mkdir(parents=True, exist_ok=True)
+    n = len(chunks)
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    shards = split_tasks(n, shard_rows)
+    pretok = n > 0 and "input_ids" in chunks[0]
+    dim = None
+    for i, start, stop in tasks_of_rank(shards, rank, world):
+        emb_file, meta_file = out / f"embeddings_batch_{i:04d}.npy", out / f"metadata_batch_{i:04d}.json"
+        if emb_file.exists() and meta_file.exists():
+            continue  # resume: this shard was completed by an earlier run
+        part = chunks[start:stop]
+        if pretok:
+            S = max(len(c["input_ids"]) for c in part)
+            ids = np.ones((len(part), S), np.int32)
+            mask = np.zeros((len(part), S), np.int32)
+            for r_, c in enumerate(part):
+                L = len(c["input_ids"])
+                ids[r_, :L] = c["input_ids"]
+                mask[r_, :L] = c.get("attention_mask", np.ones(L, np.int32))
+            payload = (ids, mask)
+        else:
+            payload = [c["text"] for c in part]
+        _, rows, err = generate_embeddings_worker((payload, model_name, batch_size, i))
+        if err:
+            raise RuntimeError(err)
+        arr = _as_matrix(rows)
+        dim = int(arr.shape[1])
+        metadata = []
+        for j, chunk in enumerate(part):
+            row = _meta_row(chunk, start + j)
+            row["batch_index"] = i
+            row["batch_position"] = j
+            metadata.append(row)
+        tmp_e, tmp_m = emb_file.with_suffix(".npy.tmp"), meta_file.with_suffix(".json.tmp")
+        with open(tmp_e, "wb") as f:
+            np.save(f, arr)
+        with open(tmp_m, "w", encoding="utf-8") as f:
+            json.dump(metadata, f, indent=2, ensure_ascii=False)
+        os.replace(tmp_m, meta_file)
+        os.replace(tmp_e, emb_file)  # the .npy appears last: its presence marks the shard complete
+    if world > 1:
+        dist.barrier()
+    index = {"total_embeddings": n, "embedding_dimension": dim, "num_batches": len(shards), "batch_size": shard_rows,
+             "chunks": [c.get("chunk_id") for c in chunks]}
+    if rank == 0:
+        if index["embedding_dimension"] is None and shards:
+            index["embedding_dimension"] = int(np.load(out / "embeddings_batch_0000.npy", mmap_mode="r").shape[1])
+        tmp = out / "index.json.tmp"
+        with open(tmp, "w", encoding="utf-8") as f:
+            json.dump(index, f, indent=2)
+        os.replace(tmp, out / "index.json")
+    if world > 1:
+        dist.barrier()
+    return index

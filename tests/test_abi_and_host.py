@@ -38,6 +38,34 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_lib.MpnetWeights) == 6 * C.sizeof(C.c_void_p)
 
 
+def integration_stub(which: str) -> str:
+    """The fenced python block that follows `<!-- stub:<which> -->` in INTEGRATION.md, verbatim."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md"), encoding="utf-8").read()
+    m = re.search(r"<!-- stub:%s -->\s*```python\n(.*?)```" % which, text, flags=re.S)
+    assert m, f"INTEGRATION.md has no stub block '{which}'"
+    return m.group(1)
+
+
+def test_integration_stub_binding(lib):
+    """Execute INTEGRATION.md's ctypes binding as a maintainer would paste it: it must load the
+    library and declare structs of exactly the header's sizes (the round-1 stub had lost
+    `position_mode`: 40 bytes against the header's 44)."""
+    ns: dict = {}
+    cwd = os.getcwd()
+    os.chdir(ROOT)  # the stub names the library by its path relative to the repository root
+    try:
+        exec(compile(integration_stub("binding"), "INTEGRATION.md:stub:binding", "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    assert C.sizeof(ns["ArbMpnetConfig"]) == C.sizeof(_lib.MpnetConfig) == 44
+    assert [f[0] for f in ns["ArbMpnetConfig"]._fields_] == [f[0] for f in _lib.MpnetConfig._fields_]
+    assert C.sizeof(ns["ArbMpnetLayerWeights"]) == C.sizeof(_lib.MpnetLayerWeights)
+    assert C.sizeof(ns["ArbMpnetWeights"]) == C.sizeof(_lib.MpnetWeights)
+    assert (ns["ARB_DTYPE_F32"], ns["ARB_DTYPE_BF16"], ns["ARB_DTYPE_F16"]) == (_lib.ARB_DTYPE_F32, _lib.ARB_DTYPE_BF16, _lib.ARB_DTYPE_F16)
+    with pytest.raises(RuntimeError):
+        ns["check"](ns["lib"].arb_mpnet_encode(0, 0, 0, 1, 1, 0, 0))
+
+
 def test_argument_errors_return_codes_not_crashes(lib):
     assert lib.arb_topk_search_workspace_bytes(_lib.ARB_DTYPE_BF16, 0, 10, 768, 10) == 0
     assert lib.arb_topk_search_workspace_bytes(_lib.ARB_DTYPE_BF16, 128, 1_000_000, 768, 10) > 0
@@ -78,6 +106,47 @@ def test_product_never_imports_oracle():
 def _chunks(n):
     return [{"chunk_id": f"2101.{i:05d}_chunk_{i % 3}", "text": f"text {i} é", "metadata":
              {"paper_id": f"2101.{i:05d}", "section": "intro", "quality_score": 0.9 + 0.001 * i}} for i in range(n)]
+
+
+def _dir_bytes(d):
+    return {f.name: f.read_bytes() for f in sorted(__import__("pathlib").Path(d).iterdir())}
+
+
+def test_layouts_byte_identical_to_reference_writers(tmp_path):
+    """The saved embedding/ID layout is half of the drop-in contract. tests/golden/layout_* were
+    written by the reference's OWN writers (tools/make_layout_golden.py: save_embeddings_to_disk.py
+    imported, generate_embeddings_parallel.py:271-321 executed from the mounted reference); every
+    writer of this repo must reproduce them byte for byte — and, where the reference is mounted, the
+    fixtures are re-minted and must not have drifted."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_layout_golden", os.path.join(ROOT, "tools", "make_layout_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    golden = os.path.join(ROOT, "tests", "golden")
+    chunks, rows = mk.fixture_inputs()
+    want_b, want_s = _dir_bytes(os.path.join(golden, "layout_batched")), _dir_bytes(os.path.join(golden, "layout_single"))
+    assert set(want_b) == {"index.json"} | {f"{k}_batch_{i:04d}.{e}" for i in range(3) for k, e in (("embeddings", "npy"), ("metadata", "json"))}
+    storage.save_embeddings_disk(chunks, rows, str(tmp_path / "b"), batch_size=3)
+    assert _dir_bytes(tmp_path / "b") == want_b
+    storage.save_embeddings_to_disk_fallback(chunks, rows, str(tmp_path / "s"))
+    assert _dir_bytes(tmp_path / "s") == want_s
+    w = storage.StreamingShardWriter(str(tmp_path / "w"), batch_size=3, float32_sidecar=False)
+    w.append(chunks[:5], rows[:5])
+    w.append(chunks[5:], rows[5:])
+    w.close()
+    assert _dir_bytes(tmp_path / "w") == want_b
+    generation._worker_model, generation._worker_model_name = type("M", (), {"encode": lambda self, b, **kw: np.stack([rows[int(r[0])] for r in b[0]])})(), "all-mpnet-base-v2"
+    try:
+        tok = [dict(c, input_ids=[i]) for i, c in enumerate(chunks)]
+        generation.generate_embeddings_to_disk(tok, str(tmp_path / "g"), batch_size=2, shard_rows=3)
+    finally:
+        generation.configure_worker_model()
+    assert _dir_bytes(tmp_path / "g") == want_b
+    if os.path.isdir(mk.REF):  # dev container: pin the fixtures to the reference itself
+        mk.main(tmp_path / "ref")
+        assert _dir_bytes(tmp_path / "ref" / "layout_batched") == want_b
+        assert _dir_bytes(tmp_path / "ref" / "layout_single") == want_s
 
 
 def test_single_file_layout_matches_reference(tmp_path):
@@ -195,7 +264,7 @@ dist.all_gather(gs, torch.from_numpy(ls)); dist.all_gather(gi, torch.from_numpy(
 ms, mi = so.merge_topk(torch.stack(gs).numpy(), torch.stack(gi).numpy())
 fs, fi = so.oracle_search(q, c, k)
 assert (mi == fi).all() and np.allclose(ms, fs, atol=1e-6), "sharded != unsharded"
-# --- encode protocol: round-robin tasks, all_gather_object, reorder (with a stub model)
+# --- encode protocol: round-robin tasks, fixed-shape tensor gather, reorder (with a stub model)
 class Stub:
     def encode(self, batch, **kw):
         ids = batch[0]
@@ -204,6 +273,29 @@ generation._worker_model, generation._worker_model_name = Stub(), "all-mpnet-bas
 chunks = [{"input_ids": [i, 5, 2]} for i in range(23)]
 rows = generation.generate_embeddings_parallel(chunks, batch_size=4, chunks_per_worker=5)
 assert len(rows) == 23 and [int(r[0]) for r in rows] == list(range(23)), "row order"
+assert rows[7].dtype == np.float32 and rows[7].shape == (4,)
+# --- data-parallel output path: every rank writes its own shards of the reference's batched layout
+from arxiv_rag_b200 import storage
+out_dir = os.environ["ARB_OUT"]
+chunks = [{"chunk_id": f"c{i}", "input_ids": [i, 5, 2], "text": f"t{i}", "metadata": {"paper_id": f"p{i}", "section": "s", "quality_score": 0.95}} for i in range(23)]
+idx = generation.generate_embeddings_to_disk(chunks, out_dir, batch_size=4, shard_rows=5)
+assert idx["num_batches"] == 5 and idx["total_embeddings"] == 23
+emb, meta = storage.load_embeddings_from_disk(out_dir)   # the reference loader's layout
+assert emb.shape == (23, 4) and emb.dtype == np.float64 and [int(r[0]) for r in emb] == list(range(23))
+assert [m["chunk_id"] for m in meta] == [f"c{i}" for i in range(23)] and meta[12]["batch_index"] == 2 and meta[12]["batch_position"] == 2
+mine = [i for i in range(5) if i % world == rank]
+dist.barrier()
+if rank == 0:
+    # resume: drop one shard, rerun -> only that shard is encoded again
+    os.remove(os.path.join(out_dir, "embeddings_batch_0003.npy"))
+dist.barrier()
+calls = []
+orig = generation.generate_embeddings_worker
+generation.generate_embeddings_worker = lambda a: (calls.append(a[3]), orig(a))[1]
+generation.generate_embeddings_to_disk(chunks, out_dir, batch_size=4, shard_rows=5)
+assert calls == ([3] if 3 % world == rank else []), calls
+emb2, _ = storage.load_embeddings_from_disk(out_dir)
+assert np.array_equal(emb, emb2)
 dist.barrier()
 if rank == 0: print("GLOO_OK")
 """
@@ -212,7 +304,7 @@ if rank == 0: print("GLOO_OK")
 def test_world_size_2_gloo(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_GLOO_WORKER)
-    env = dict(os.environ, ARB_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    env = dict(os.environ, ARB_ROOT=ROOT, MASTER_ADDR="127.0.0.1", ARB_OUT=str(tmp_path / "shards"))
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
                          capture_output=True, text=True, env=env, timeout=240)

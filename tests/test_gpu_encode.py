@@ -326,3 +326,64 @@ def test_full_size_batch_properties(cuda, full_model):
     ref = eo.oracle_encode(model, ids[:4], mask[:4], batch_size=4)
     assert _cos(big[:4], ref).min() >= COS_TOL
     enc.close()
+
+
+def test_encode_from_strings(cuda, tmp_path):
+    """`model.encode(List[str], ...)` as the reference calls it (generate_embeddings_parallel.py:146-153):
+    in-tree tokenizer from a vocab file, sort by text length, per-batch padding, background
+    tokenisation — equal to tokenising by hand and encoding the ids, in input order, and equal to
+    the oracle model fed by transformers' own tokenizer."""
+    from transformers import MPNetTokenizer
+
+    from tests.test_tokenizer import TEXTS, VOCAB, _random_texts
+
+    arch = MPNetArch(vocab_size=len(VOCAB), num_layers=2)
+    sd = synthetic_state_dict(arch, 4)
+    vf = tmp_path / "vocab.txt"
+    vf.write_text("\n".join(VOCAB) + "\n", encoding="utf-8")
+    enc = _encoder(arch, sd, "fp16", max_batch=16, max_seq=48, vocab_file=str(vf))
+    texts = TEXTS + _random_texts(60, seed=3)
+    got = enc.encode(texts, batch_size=7, normalize_embeddings=True, show_progress_bar=False, convert_to_numpy=True)
+    assert got.shape == (len(texts), 768) and got.dtype == np.float32
+    hf = MPNetTokenizer(vocab=VOCAB)
+    tk = hf(texts, padding=True, truncation=True, max_length=48, return_tensors="np")
+    ref = eo.oracle_encode(eo.reference_model(arch, sd), tk["input_ids"], tk["attention_mask"])
+    assert _cos(got, ref).min() >= COS_TOL
+    one = enc.encode(texts[0])
+    assert one.shape == (768,) and np.abs(one - got[0]).max() < 1e-6
+    enc.close()
+
+
+def test_integration_stub_runs(cuda, full_model):
+    """INTEGRATION.md's two ctypes blocks, executed verbatim against the built library: the encode
+    result must equal the Python mirror's, the search result CorpusIndex's."""
+    import ctypes as C
+
+    import torch
+
+    from arxiv_rag_b200.search import CorpusIndex
+    from arxiv_rag_b200.weights import PackedWeights
+    from tests.conftest import ROOT
+    from tests.test_abi_and_host import integration_stub
+
+    arch, sd, _ = full_model
+    packed = PackedWeights(arch, sd)
+    ids, mask = eo.synthetic_tokens(5, 40, seed=8)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    corpus = torch.nn.functional.normalize(torch.randn(3000, 768, device=cuda, generator=g), dim=1).to(torch.bfloat16)
+    q = torch.nn.functional.normalize(torch.randn(9, 768, device=cuda, generator=g), dim=1).to(torch.bfloat16)
+    ns = {"weights": packed.struct, "input_ids": ids, "attention_mask": mask, "q": q, "corpus": corpus, "Q": 9, "N": 3000, "id_offset": 100}
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        exec(compile(integration_stub("binding"), "INTEGRATION.md:stub:binding", "exec"), ns)
+        exec(compile(integration_stub("usage"), "INTEGRATION.md:stub:usage", "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    torch.cuda.synchronize()
+    enc = _encoder(arch, sd, "fp16", max_batch=8, max_seq=64)
+    want = enc.encode_tokens(torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda())
+    assert torch.equal(ns["out"], want)
+    enc.close()
+    ws_, wi_ = CorpusIndex(corpus, id_offset=100).search(q, 10)
+    assert torch.equal(ns["scores"], ws_) and torch.equal(ns["idx"], wi_)
