@@ -81,6 +81,8 @@ SIGNATURES = {
     "arb_mpnet_relative_bucket": (C.c_int, [_I32, _I32, _I32]),
     "arb_topk_search_workspace_bytes": (_SZ, [_I32, _I64, _I64, _I32, _I32]),
     "arb_topk_search": (C.c_int, [_VP, _VP, _I32, _I64, _I64, _I32, _I32, _VP, _VP, _I64, _VP, _SZ, _VP]),
+    "arb_topk_search_f32_workspace_bytes": (_SZ, [_I64, _I64, _I32, _I32, _I32]),
+    "arb_topk_search_f32": (C.c_int, [_VP, _VP, _I64, _I64, _I32, _I32, _F, _VP, _VP, _I64, _VP, _I32, _VP, _SZ, _VP]),
     "arb_topk_merge": (C.c_int, [_VP, _VP, _I32, _I64, _I32, _VP, _VP, _VP]),
     "arb_topk_search_launches": (C.c_int, [_I32]),
     "arb_set_gemm_mode": (C.c_int, [_I32]),

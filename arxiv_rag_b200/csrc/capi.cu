@@ -440,8 +440,20 @@ int arb_mpnet_status(void* handle) {
 
 size_t arb_topk_search_workspace_bytes(int32_t dtype, int64_t Q, int64_t N, int32_t D, int32_t k) {
     if (dtype == ARB_DTYPE_BF16) return search_workspace_bytes(Q, N, D, k);
-    if (dtype == ARB_DTYPE_F32) return search_f32_workspace_bytes(Q, N, D, k);
+    if (dtype == ARB_DTYPE_F32) return search_f32_workspace_bytes(Q, N, D, k, 0);
     return 0;
+}
+
+size_t arb_topk_search_f32_workspace_bytes(int64_t Q, int64_t N, int32_t D, int32_t k, int32_t mode) {
+    return search_f32_workspace_bytes(Q, N, D, k, mode);
+}
+
+int arb_topk_search_f32(const float* queries_dev, const float* corpus_dev, int64_t Q, int64_t N, int32_t D, int32_t k,
+                        float corpus_max_norm, float* out_scores_dev, int64_t* out_ids_dev, int64_t id_offset,
+                        int32_t* unverified_dev, int32_t mode, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    ARB_REQUIRE(corpus_max_norm > 0.f && corpus_max_norm < 1e30f, "search_f32: corpus_max_norm must be a positive bound of the row norms");
+    return launch_search_f32(queries_dev, corpus_dev, Q, N, D, k, corpus_max_norm, out_scores_dev, out_ids_dev, id_offset,
+                             unverified_dev, mode, workspace_dev, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int arb_topk_search(const void* queries_dev, const void* corpus_dev, int32_t dtype, int64_t Q,
@@ -454,14 +466,14 @@ int arb_topk_search(const void* queries_dev, const void* corpus_dev, int32_t dty
                                   out_scores_dev, out_ids_dev, id_offset, workspace_dev, workspace_bytes, st);
     if (dtype == ARB_DTYPE_F32)
         return launch_search_f32(static_cast<const float*>(queries_dev), static_cast<const float*>(corpus_dev),
-                                 Q, N, D, k, out_scores_dev, out_ids_dev, id_offset, workspace_dev,
+                                 Q, N, D, k, 1.0f, out_scores_dev, out_ids_dev, id_offset, nullptr, 0, workspace_dev,
                                  workspace_bytes, st);
     set_error("topk_search: unknown dtype %d", dtype);
     return ARB_ERR_INVALID;
 }
 
-// search kernel + split merge (+ the query pad copy when Q is not a whole number of tiles; + split x2 and re-score for fp32)
-int arb_topk_search_launches(int32_t dtype) { return dtype == ARB_DTYPE_F32 ? 6 : 3; }
+// search kernel + split merge (+ the query pad copy when Q is not a whole number of tiles; + the re-score for fp32)
+int arb_topk_search_launches(int32_t dtype) { return dtype == ARB_DTYPE_F32 ? 4 : 3; }
 
 int arb_topk_merge(const float* scores_dev, const int64_t* ids_dev, int32_t G, int64_t Q, int32_t k,
                    float* out_scores_dev, int64_t* out_ids_dev, void* stream) {

@@ -85,11 +85,14 @@ size_t search_workspace_bytes(int64_t Q, int64_t N, int D, int k);
 int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int64_t Q, int64_t N,
                        int D, int k, float* out_scores, int64_t* out_ids, int64_t id_offset,
                        void* workspace, size_t ws_bytes, cudaStream_t stream);
-// fp32 operands: bf16 hi/lo split scoring + exact fp32 re-score of the candidates.
-size_t search_f32_workspace_bytes(int64_t Q, int64_t N, int D, int k);
+// fp32 operands. mode 0: one kind::tf32 pass over the stored rows, k + 22 candidates re-scored in exact
+// fp32, and a per-query verdict whether the result is provably the exact top-k (unverified[q] = 1 -> the
+// caller re-runs that query with mode 1). mode 1: 3-term bf16 hi/lo split (error ~4e-7) + re-score.
+// corpus_max_norm: upper bound of the corpus rows' L2 norms (1 for unit rows), used by the verdict.
+size_t search_f32_workspace_bytes(int64_t Q, int64_t N, int D, int k, int mode);
 int launch_search_f32(const float* q, const float* corpus, int64_t Q, int64_t N, int D, int k,
-                      float* out_scores, int64_t* out_ids, int64_t id_offset, void* workspace,
-                      size_t ws_bytes, cudaStream_t stream);
+                      float corpus_max_norm, float* out_scores, int64_t* out_ids, int64_t id_offset,
+                      int32_t* unverified, int mode, void* workspace, size_t ws_bytes, cudaStream_t stream);
 // k-way merge of G per-shard top-k lists: [G,Q,k] -> [Q,k], order (score desc, id asc).
 int launch_topk_merge(const float* scores, const int64_t* ids, int G, int64_t Q, int k,
                       float* out_scores, int64_t* out_ids, cudaStream_t stream);

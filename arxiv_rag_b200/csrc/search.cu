@@ -177,7 +177,9 @@ __device__ __forceinline__ void reg_insert(float (&s)[KR], int (&id)[KR], float 
 // every CTA stages only half of the chunk (32 KB stages -> a deeper ring beside large lists, half
 // the L2 -> SM corpus traffic) and keeps the lists of its own 128 query rows. `nq` then counts
 // query-tile pairs.
-template <int kSStages, int KR, bool kPair>
+// kTf32: the operands are fp32 rows (D = 16-bit words per row = 2 x the fp32 width) scored with
+// kind::tf32 MMAs.
+template <int kSStages, int KR, bool kPair, bool kTf32 = false>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                    const __grid_constant__ CUtensorMap tmap_c, float* __restrict__ part_scores,
@@ -208,9 +210,12 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     } else if (warp == 1) {
         if (elect_one()) {
             if constexpr (kPair) {
-                if (rank == 0) pipe2_mma<SM>(sm, tmem_base, it, kblocks, umma_idesc_16bit(2 * kBM, SM::kBN, false));
+                if (rank == 0)
+                    pipe2_mma<SM, kTf32>(sm, tmem_base, it, kblocks,
+                                         kTf32 ? umma_idesc_tf32(2 * kBM, SM::kBN) : umma_idesc_16bit(2 * kBM, SM::kBN, false));
             } else {
-                pipe_mma<SM>(sm, tmem_base, it, kblocks, umma_idesc_16bit(kBM, SM::kBN, false));
+                pipe_mma<SM, kTf32>(sm, tmem_base, it, kblocks,
+                                    kTf32 ? umma_idesc_tf32(kBM, SM::kBN) : umma_idesc_16bit(kBM, SM::kBN, false));
             }
         }
     } else {
@@ -837,9 +842,10 @@ size_t search_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
     return align_up(per * 4, 256) + align_up(per * 4, 256) + align_up(pad, 256);
 }
 
-int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int64_t Q, int64_t N,
-                       int D, int k, float* out_scores, int64_t* out_ids, int64_t id_offset,
-                       void* workspace, size_t ws_bytes, cudaStream_t stream) {
+// q / corpus: rows of D 16-bit words (bf16 values, or — tf32 — the two halves of D/2 fp32 values).
+static int launch_search_16(const uint16_t* q, const uint16_t* corpus, int64_t Q, int64_t N,
+                            int D, int k, float* out_scores, int64_t* out_ids, int64_t id_offset,
+                            void* workspace, size_t ws_bytes, bool tf32, cudaStream_t stream) {
     ARB_REQUIRE(q && corpus && out_scores && out_ids, "search: null pointer");
     ARB_REQUIRE(Q > 0 && N > 0, "search: empty problem Q=%lld N=%lld", (long long)Q, (long long)N);
     ARB_REQUIRE(D > 0 && D % 8 == 0, "search: D=%d must be a positive multiple of 8", D);
@@ -859,7 +865,7 @@ int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int6
 
     const int64_t Qp = padded_queries(Q, p.pair);
     if (Qp > 0) {  // whole query tiles only: see padded_queries
-        __nv_bfloat16* qpad = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + 2 * align_up(per * 4, 256));
+        uint16_t* qpad = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(workspace) + 2 * align_up(per * 4, 256));
         const int64_t total = Qp * D / 8, valid = Q * D / 8;
         const int blocks = static_cast<int>(total < 148ll * 8 * 256 ? (total + 255) / 256 : 148 * 8);
         pad_queries_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(q), reinterpret_cast<uint4*>(qpad), valid, total);
@@ -903,13 +909,28 @@ int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int6
         return ARB_OK;
     };
     int lrc;
-    if (p.pair) {
-        // 32 KB stages (query tile + half a corpus chunk per CTA): the deepest ring that leaves the
-        // lists and a >= 16-candidate buffer in place
-        constexpr int kP6 = PipeSmem<kSBN, 6, 0, 2>::kExtraOffset, kP5 = PipeSmem<kSBN, 5, 0, 2>::kExtraOffset,
-                      kP4 = PipeSmem<kSBN, 4, 0, 2>::kExtraOffset, kP3 = PipeSmem<kSBN, 3, 0, 2>::kExtraOffset,
-                      kP2 = PipeSmem<kSBN, 2, 0, 2>::kExtraOffset;
-        static_assert((kSmemMax - 1024 - kP6) / (kBM * 8) >= 33, "register-list kernels need a 32-candidate buffer");
+    // 32 KB stages for the pair schedule (query tile + half a corpus chunk per CTA): the deepest ring
+    // that leaves the lists and a >= 16-candidate buffer in place
+    constexpr int kP6 = PipeSmem<kSBN, 6, 0, 2>::kExtraOffset, kP5 = PipeSmem<kSBN, 5, 0, 2>::kExtraOffset,
+                  kP4 = PipeSmem<kSBN, 4, 0, 2>::kExtraOffset, kP3 = PipeSmem<kSBN, 3, 0, 2>::kExtraOffset,
+                  kP2 = PipeSmem<kSBN, 2, 0, 2>::kExtraOffset;
+    constexpr int kRing4 = PipeSmem<kSBN, 4>::kExtraOffset, kRing3 = PipeSmem<kSBN, 3>::kExtraOffset,
+                  kRing2 = PipeSmem<kSBN, 2>::kExtraOffset;
+    static_assert((kSmemMax - 1024 - kP6) / (kBM * 8) >= 33, "register-list kernels need a 32-candidate buffer");
+    static_assert((kSmemMax - 1024 - kRing4) / (kBM * 8) >= 33, "register-list kernels need a 32-candidate buffer");
+    if (tf32) {  // fp32 operands (the callers over-select, so k is never tiny: no KR = 10 variant)
+        if (p.pair) {
+            if (k <= 16) lrc = launch(search_topk_kernel<6, 16, true, true>, kP6, 0, 32);
+            else if (buffer_for(kP5, k) >= 16) lrc = launch(search_topk_kernel<5, 0, true, true>, kP5, k, buffer_for(kP5, k));
+            else if (buffer_for(kP4, k) >= 16) lrc = launch(search_topk_kernel<4, 0, true, true>, kP4, k, buffer_for(kP4, k));
+            else if (buffer_for(kP3, k) >= 16) lrc = launch(search_topk_kernel<3, 0, true, true>, kP3, k, buffer_for(kP3, k));
+            else lrc = launch(search_topk_kernel<2, 0, true, true>, kP2, k, buffer_for(kP2, k));
+        } else {
+            if (k <= 16) lrc = launch(search_topk_kernel<4, 16, false, true>, kRing4, 0, 32);
+            else if (buffer_for(kRing3, k) >= 16) lrc = launch(search_topk_kernel<3, 0, false, true>, kRing3, k, buffer_for(kRing3, k));
+            else lrc = launch(search_topk_kernel<2, 0, false, true>, kRing2, k, buffer_for(kRing2, k));
+        }
+    } else if (p.pair) {
         if (k <= 10) lrc = launch(search_topk_kernel<6, 10, true>, kP6, 0, 32);
         else if (k <= 16) lrc = launch(search_topk_kernel<6, 16, true>, kP6, 0, 32);
         else if (buffer_for(kP5, k) >= 16) lrc = launch(search_topk_kernel<5, 0, true>, kP5, k, buffer_for(kP5, k));
@@ -917,9 +938,6 @@ int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int6
         else if (buffer_for(kP3, k) >= 16) lrc = launch(search_topk_kernel<3, 0, true>, kP3, k, buffer_for(kP3, k));
         else lrc = launch(search_topk_kernel<2, 0, true>, kP2, k, buffer_for(kP2, k));
     } else {
-        constexpr int kRing4 = PipeSmem<kSBN, 4>::kExtraOffset, kRing3 = PipeSmem<kSBN, 3>::kExtraOffset,
-                      kRing2 = PipeSmem<kSBN, 2>::kExtraOffset;
-        static_assert((kSmemMax - 1024 - kRing4) / (kBM * 8) >= 33, "register-list kernels need a 32-candidate buffer");
         if (k <= 10) lrc = launch(search_topk_kernel<4, 10, false>, kRing4, 0, 32);
         else if (k <= 16) lrc = launch(search_topk_kernel<4, 16, false>, kRing4, 0, 32);
         else if (buffer_for(kRing3, k) >= 16) lrc = launch(search_topk_kernel<3, 0, false>, kRing3, k, buffer_for(kRing3, k));
@@ -931,14 +949,31 @@ int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int6
                                       out_ids, stream);
 }
 
+int launch_search_bf16(const __nv_bfloat16* q, const __nv_bfloat16* corpus, int64_t Q, int64_t N,
+                       int D, int k, float* out_scores, int64_t* out_ids, int64_t id_offset,
+                       void* workspace, size_t ws_bytes, cudaStream_t stream) {
+    return launch_search_16(reinterpret_cast<const uint16_t*>(q), reinterpret_cast<const uint16_t*>(corpus), Q, N, D, k,
+                            out_scores, out_ids, id_offset, workspace, ws_bytes, false, stream);
+}
+
 // ----------------------------------------------------------------------------- fp32 search
-// fp32 operands are scored on the bf16 tensor cores through a hi/lo split folded into K:
+// Two ways to score fp32 operands on the tensor cores; both over-select, re-score the candidates
+// with exact fp32 FMAs and re-rank, so the returned scores are true fp32 dot products.
+//
+// mode 0 (default): ONE kind::tf32 pass straight over the stored fp32 rows — no converted copy of the
+//   corpus, no extra memory. tf32 keeps 10 mantissa bits: |approx - exact| <= 2^-9 |q| |c| for every
+//   row (each operand off by < 2^-10 relative, Cauchy-Schwarz). The k + kTf32Margin best approximate
+//   scores are re-scored; the result is then PROVABLY the exact top-k iff the exact k-th best score
+//   t_k and the worst approximate candidate score a_min satisfy t_k >= a_min + eps, eps = 2^-9 |q|
+//   max|c| (no row outside the candidate list can reach t_k). The re-score kernel writes that verdict
+//   per query (`unverified`); the host re-runs the few unverified queries through mode 1.
+// mode 1 (exact fallback): hi/lo split folded into K,
 //   x = hi + lo (both bf16, |x - hi - lo| <= 2^-17 |x|),
 //   q.c ~= q_hi.c_hi + q_lo.c_hi + q_hi.c_lo = [q_hi | q_lo | q_hi] . [c_hi | c_hi | c_lo]
-// i.e. one bf16 search with D' = 3D (error ~4e-7 on unit vectors of dim 768, well inside the
-// 1e-5 tie tolerance). The k + kF32Margin survivors are then re-scored with exact fp32 FMAs and
-// re-ranked, so the returned scores are true fp32 dot products.
-constexpr int kF32Margin = 8;
+//   i.e. one bf16 search with D' = 3D (error ~4e-7 on unit vectors of dim 768, well inside the 1e-5
+//   tie tolerance) at 3x the MMA work and a 1.5x copy of the corpus in the workspace.
+constexpr int kF32Margin = 8;     // mode 1
+constexpr int kTf32Margin = 22;   // mode 0: k = 10 -> 32 candidates
 
 template <bool kIsQuery>
 __global__ void __launch_bounds__(256)
@@ -969,10 +1004,13 @@ split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, 
 }
 
 // One warp per query: exact fp32 dot for each candidate, then rank by (score desc, id asc).
+// verify_scale > 0 (mode 0): also decide whether the candidate list provably contains the exact
+// top-k: unverified[q] = 1 iff the list is full and t_k < a_min + verify_scale * |q|.
 __global__ void __launch_bounds__(128)
 rescore_f32_kernel(const float* __restrict__ q, const float* __restrict__ corpus, int64_t Q, int D,
-                   int kc, int k, const int64_t* __restrict__ cand_ids, int64_t id_offset,
-                   float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+                   int kc, int k, const float* __restrict__ cand_scores, const int64_t* __restrict__ cand_ids,
+                   int64_t id_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+                   float verify_scale, int32_t* __restrict__ unverified) {
     extern __shared__ uint8_t smem_rs[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     float* sc = reinterpret_cast<float*>(smem_rs) + warp * kc;
@@ -981,6 +1019,15 @@ rescore_f32_kernel(const float* __restrict__ q, const float* __restrict__ corpus
     const int64_t qi = static_cast<int64_t>(blockIdx.x) * nw + warp;
     if (qi >= Q) return;
     const float* qr = q + qi * D;
+    float qn2 = 0.f;  // |q|^2 (mode 0)
+    if (verify_scale > 0.f) {
+        for (int d = lane * 4; d < D; d += 128) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(qr + d));
+            qn2 = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, qn2))));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) qn2 += __shfl_xor_sync(0xffffffff, qn2, o);
+    }
     for (int c = 0; c < kc; ++c) {
         const int64_t id = cand_ids[qi * kc + c];  // already offset by id_offset
         float acc = 0.f;
@@ -1003,6 +1050,7 @@ rescore_f32_kernel(const float* __restrict__ q, const float* __restrict__ corpus
         }
     }
     __syncwarp();
+    float tk = INFINITY;  // exact score that lands at rank k - 1
     for (int c = lane; c < kc; c += 32) {
         const float s = sc[c];
         const int64_t id = si[c];
@@ -1018,61 +1066,88 @@ rescore_f32_kernel(const float* __restrict__ q, const float* __restrict__ corpus
             out_scores[qi * k + rank] = s;
             out_ids[qi * k + rank] = id;
         }
+        if (rank == k - 1) tk = s;
+    }
+    if (unverified != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tk = fminf(tk, __shfl_xor_sync(0xffffffff, tk, o));
+        if (lane == 0) {
+            // the approximate lists are sorted: the last slot is the worst candidate; an unused last
+            // slot means every corpus row is a candidate
+            const bool full = cand_ids[qi * kc + kc - 1] >= 0;
+            const float a_min = cand_scores[qi * kc + kc - 1];
+            unverified[qi] = (full && !(tk >= a_min + verify_scale * sqrtf(qn2))) ? 1 : 0;
+        }
     }
 }
 
-static void f32_layout(int64_t Q, int64_t N, int D, int k, size_t* off_q, size_t* off_c, size_t* off_cs,
+static int f32_kc(int k, int mode) {
+    const int kc = k + (mode == 0 ? kTf32Margin : kF32Margin);
+    return kc < kMaxK ? kc : kMaxK;
+}
+
+static void f32_layout(int64_t Q, int64_t N, int D, int k, int mode, size_t* off_q, size_t* off_c, size_t* off_cs,
                        size_t* off_ci, size_t* off_inner, size_t* total) {
-    const int kc = k + kF32Margin < kMaxK ? k + kF32Margin : kMaxK;
+    const int kc = f32_kc(k, mode);
     size_t o = 0;
-    *off_q = o;  o += align_up(static_cast<size_t>(Q) * 3 * D * 2, 256);
-    *off_c = o;  o += align_up(static_cast<size_t>(N) * 3 * D * 2, 256);
+    *off_q = o;  o += mode == 0 ? 0 : align_up(static_cast<size_t>(Q) * 3 * D * 2, 256);
+    *off_c = o;  o += mode == 0 ? 0 : align_up(static_cast<size_t>(N) * 3 * D * 2, 256);
     *off_cs = o; o += align_up(static_cast<size_t>(Q) * kc * 4, 256);
     *off_ci = o; o += align_up(static_cast<size_t>(Q) * kc * 8, 256);
-    *off_inner = o; o += search_workspace_bytes(Q, N, 3 * D, kc);
+    *off_inner = o; o += search_workspace_bytes(Q, N, mode == 0 ? 2 * D : 3 * D, kc);
     *total = o;
 }
 
-size_t search_f32_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
-    if (Q <= 0 || N <= 0 || k <= 0 || D <= 0) return 0;
+size_t search_f32_workspace_bytes(int64_t Q, int64_t N, int D, int k, int mode) {
+    if (Q <= 0 || N <= 0 || k <= 0 || D <= 0 || mode < 0 || mode > 1) return 0;
     size_t a, b, c, d, e, t;
-    f32_layout(Q, N, D, k, &a, &b, &c, &d, &e, &t);
+    f32_layout(Q, N, D, k, mode, &a, &b, &c, &d, &e, &t);
     return t;
 }
 
 int launch_search_f32(const float* q, const float* corpus, int64_t Q, int64_t N, int D, int k,
-                      float* out_scores, int64_t* out_ids, int64_t id_offset, void* workspace,
-                      size_t ws_bytes, cudaStream_t stream) {
+                      float corpus_max_norm, float* out_scores, int64_t* out_ids, int64_t id_offset,
+                      int32_t* unverified, int mode, void* workspace, size_t ws_bytes, cudaStream_t stream) {
     ARB_REQUIRE(q && corpus && out_scores && out_ids, "search_f32: null pointer");
     ARB_REQUIRE(Q > 0 && N > 0, "search_f32: empty problem Q=%lld N=%lld", (long long)Q, (long long)N);
     ARB_REQUIRE(D > 0 && D % 8 == 0, "search_f32: D=%d must be a positive multiple of 8", D);
     ARB_REQUIRE(k > 0 && k <= kMaxK, "search_f32: k=%d out of range [1,%d]", k, kMaxK);
+    ARB_REQUIRE(mode == 0 || mode == 1, "search_f32: mode %d must be 0 (tf32 + verified re-score) or 1 (split-bf16)", mode);
     ARB_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(corpus) & 15) == 0,
                 "search_f32: operands must be 16-byte aligned");
     size_t off_q, off_c, off_cs, off_ci, off_inner, total;
-    f32_layout(Q, N, D, k, &off_q, &off_c, &off_cs, &off_ci, &off_inner, &total);
+    f32_layout(Q, N, D, k, mode, &off_q, &off_c, &off_cs, &off_ci, &off_inner, &total);
     if (workspace == nullptr || ws_bytes < total) {
         set_error("search_f32: workspace too small (%zu < %zu bytes)", ws_bytes, total);
         return ARB_ERR_WORKSPACE;
     }
-    const int kc = k + kF32Margin < kMaxK ? k + kF32Margin : kMaxK;
+    const int kc = f32_kc(k, mode);
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-    __nv_bfloat16* q3 = reinterpret_cast<__nv_bfloat16*>(ws + off_q);
-    __nv_bfloat16* c3 = reinterpret_cast<__nv_bfloat16*>(ws + off_c);
     float* cs = reinterpret_cast<float*>(ws + off_cs);
     int64_t* ci = reinterpret_cast<int64_t*>(ws + off_ci);
-    const int blocks = num_sms() * 8;
-    split_bf16_kernel<true><<<blocks, 256, 0, stream>>>(q, q3, Q, D);
-    split_bf16_kernel<false><<<blocks, 256, 0, stream>>>(corpus, c3, N, D);
-    ARB_CHECK_CUDA(cudaGetLastError());
-    int rc = launch_search_bf16(q3, c3, Q, N, 3 * D, kc, cs, ci, id_offset, ws + off_inner,
-                                ws_bytes - off_inner, stream);
+    int rc;
+    if (mode == 0) {
+        rc = launch_search_16(reinterpret_cast<const uint16_t*>(q), reinterpret_cast<const uint16_t*>(corpus), Q, N, 2 * D, kc,
+                              cs, ci, id_offset, ws + off_inner, ws_bytes - off_inner, true, stream);
+    } else {
+        __nv_bfloat16* q3 = reinterpret_cast<__nv_bfloat16*>(ws + off_q);
+        __nv_bfloat16* c3 = reinterpret_cast<__nv_bfloat16*>(ws + off_c);
+        const int blocks = num_sms() * 8;
+        split_bf16_kernel<true><<<blocks, 256, 0, stream>>>(q, q3, Q, D);
+        split_bf16_kernel<false><<<blocks, 256, 0, stream>>>(corpus, c3, N, D);
+        ARB_CHECK_CUDA(cudaGetLastError());
+        rc = launch_search_bf16(q3, c3, Q, N, 3 * D, kc, cs, ci, id_offset, ws + off_inner, ws_bytes - off_inner, stream);
+    }
     if (rc) return rc;
     const int nw = 4;
     const size_t smem = static_cast<size_t>(nw) * kc * 4 + 8 + static_cast<size_t>(nw) * kc * 8;
+    // 2^-9 |q| max|c| bounds the tf32 scoring error of any row (see the header comment); a little
+    // slack covers the fp32 accumulation order of the MMA and of the re-score
+    const float verify_scale = mode == 0 ? (1.0f / 512.0f) * corpus_max_norm * 1.001f + 1e-6f : 0.f;
     rescore_f32_kernel<<<static_cast<int>((Q + nw - 1) / nw), nw * 32, smem, stream>>>(
-        q, corpus, Q, D, kc, k, ci, id_offset, out_scores, out_ids);
+        q, corpus, Q, D, kc, k, cs, ci, id_offset, out_scores, out_ids, verify_scale, mode == 0 ? unverified : nullptr);
     ARB_CHECK_CUDA(cudaGetLastError());
+    if (mode == 1 && unverified != nullptr) ARB_CHECK_CUDA(cudaMemsetAsync(unverified, 0, static_cast<size_t>(Q) * 4, stream));
     return ARB_OK;
 }
 

@@ -118,7 +118,9 @@ __device__ __forceinline__ void pipe_produce(const SM& sm, const void* tmap_a, c
 // that the epilogue has released; commits release the smem stage and publish the accumulator.
 // idesc: umma_idesc_16bit(kBM, SM::kBN, A format, B format) — a runtime value, so one kernel serves
 // every operand-format pair.
-template <class SM, class TileIter>
+// kTf32: the 128-byte rows hold 32 fp32 values and the MMAs are kind::tf32 (4 K-steps of 8) —
+// byte layout, swizzle and descriptor stepping are the same as for 64 16-bit values.
+template <class SM, bool kTf32 = false, class TileIter>
 __device__ __forceinline__ void pipe_mma(const SM& sm, uint32_t tmem_base, TileIter it, int kblocks, uint32_t idesc) {
     int stage = 0;
     uint32_t phase = 0;
@@ -137,7 +139,8 @@ __device__ __forceinline__ void pipe_mma(const SM& sm, uint32_t tmem_base, TileI
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
                 // +32 bytes per K=16 step inside the 128-byte swizzle atom -> +2 in addr>>4 units
-                umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                if constexpr (kTf32) umma_tf32_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                else umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit(sm.empty(stage));
             if (++stage == SM::kStages) {
@@ -222,7 +225,7 @@ __device__ __forceinline__ void pipe2_produce(const SM& sm, const void* tmap_a, 
 }
 
 // MMA issuer (leader CTA only): 4 x (256 x BN x 16) per K-block.
-template <class SM, class TileIter>
+template <class SM, bool kTf32 = false, class TileIter>
 __device__ __forceinline__ void pipe2_mma(const SM& sm, uint32_t tmem_base, TileIter it, int kblocks, uint32_t idesc) {
     int stage = 0;
     uint32_t phase = 0;
@@ -242,8 +245,10 @@ __device__ __forceinline__ void pipe2_mma(const SM& sm, uint32_t tmem_base, Tile
             const uint64_t da = umma_desc_sw128(smem_u32(sm.a(stage)));
             const uint64_t db = umma_desc_sw128(smem_u32(sm.b(stage)));
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k)
-                umma_bf16_ss_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+                if constexpr (kTf32) umma_tf32_ss_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                else umma_bf16_ss_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
             umma_commit_2cta(sm.empty(stage), 0b11);
             if (++stage == SM::kStages) {
                 stage = 0;

@@ -37,8 +37,12 @@ def shard_bounds(n_rows: int, world_size: int, rank: int) -> tuple[int, int]:
 class CorpusIndex:
     """A corpus shard resident in HBM plus the reusable search workspace.
 
-    corpus : `[N, D]` float32 or bfloat16 (numpy / torch, host or device). float32 stays float32
-        (scored with the split-bf16 + fp32 re-score path); bf16 is searched as stored.
+    corpus : `[N, D]` float32 or bfloat16 (numpy / torch, host or device). bf16 is searched as
+        stored. float32 stays float32: one tf32 tensor-core pass over the stored rows, the k + 22 best
+        re-scored in exact fp32, and a per-query proof that no other row can belong to the top-k
+        (tf32 scoring is off by at most 2^-9 |q| |c|); the few queries without that proof (dense
+        near-ties around rank k) are re-run through the 3-term split-bf16 path, so the result is
+        the exact fp32 top-k either way. No converted copy of the corpus is kept.
     id_offset : global id of local row 0 (for row-sharded corpora).
     """
 
@@ -62,8 +66,17 @@ class CorpusIndex:
         self.id_offset = int(id_offset)
         self.dtype_code = _lib.ARB_DTYPE_F32 if self.corpus.dtype == torch.float32 else _lib.ARB_DTYPE_BF16
         self._ws = None
+        self.max_norm = 1.0
+        self.fallback_queries = 0  # fp32 corpora: queries that needed the exact split-bf16 re-run so far
+        if self.dtype_code == _lib.ARB_DTYPE_F32 and self.n:
+            mx = 0.0
+            for s0 in range(0, self.n, 1 << 20):  # slabs: no [N] temporary next to a large corpus
+                mx = max(mx, float(torch.linalg.vector_norm(self.corpus[s0:s0 + (1 << 20)], dim=1).max()))
+            self.max_norm = mx * (1.0 + 1e-6) + 1e-30
 
-    def workspace_bytes(self, Q: int, k: int) -> int:
+    def workspace_bytes(self, Q: int, k: int, mode: int = 0) -> int:
+        if self.dtype_code == _lib.ARB_DTYPE_F32:
+            return int(_lib.lib().arb_topk_search_f32_workspace_bytes(Q, self.n, self.d, k, mode))
         return int(_lib.lib().arb_topk_search_workspace_bytes(self.dtype_code, Q, self.n, self.d, k))
 
     def new_workspace(self, Q: int, k: int):
@@ -106,11 +119,39 @@ class CorpusIndex:
         else:
             ws, _ = self._workspace(Q, k)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().arb_topk_search(_lib.ptr(q), _lib.ptr(self.corpus), self.dtype_code, Q,
-                                                  self.n, self.d, k, _lib.ptr(out_scores), _lib.ptr(out_ids),
-                                                  self.id_offset, _lib.ptr(ws), ws.numel(),
-                                                  _lib.current_stream()))
+            if self.dtype_code == _lib.ARB_DTYPE_F32:
+                self._search_f32(q, k, out_scores, out_ids, ws)
+            else:
+                _lib.check(_lib.lib().arb_topk_search(_lib.ptr(q), _lib.ptr(self.corpus), self.dtype_code, Q,
+                                                      self.n, self.d, k, _lib.ptr(out_scores), _lib.ptr(out_ids),
+                                                      self.id_offset, _lib.ptr(ws), ws.numel(),
+                                                      _lib.current_stream()))
         return out_scores, out_ids
+
+    def _search_f32(self, q, k, out_scores, out_ids, ws):
+        """tf32 pass + exact re-score + verdict; unverified queries go through the split-bf16 path.
+        Reads one int back from the device (the number of unverified queries)."""
+        torch = self._torch
+        lib = _lib.lib()
+        Q = q.shape[0]
+        flags = torch.empty(Q, dtype=torch.int32, device=q.device)
+        _lib.check(lib.arb_topk_search_f32(_lib.ptr(q), _lib.ptr(self.corpus), Q, self.n, self.d, k, self.max_norm,
+                                           _lib.ptr(out_scores), _lib.ptr(out_ids), self.id_offset, _lib.ptr(flags), 0,
+                                           _lib.ptr(ws), ws.numel(), _lib.current_stream()))
+        bad = torch.nonzero(flags, as_tuple=False).flatten()  # synchronises
+        if bad.numel() == 0:
+            return
+        self.fallback_queries += int(bad.numel())
+        qb = q[bad].contiguous()
+        need = self.workspace_bytes(int(bad.numel()), k, mode=1)
+        ws1 = torch.empty(max(need, 256), dtype=torch.uint8, device=q.device)
+        s1 = torch.empty((bad.numel(), k), dtype=torch.float32, device=q.device)
+        i1 = torch.empty((bad.numel(), k), dtype=torch.int64, device=q.device)
+        _lib.check(lib.arb_topk_search_f32(_lib.ptr(qb), _lib.ptr(self.corpus), int(bad.numel()), self.n, self.d, k,
+                                           self.max_norm, _lib.ptr(s1), _lib.ptr(i1), self.id_offset, 0, 1,
+                                           _lib.ptr(ws1), ws1.numel(), _lib.current_stream()))
+        out_scores[bad] = s1
+        out_ids[bad] = i1
 
     @property
     def launches_per_search(self) -> int:

@@ -131,12 +131,26 @@ int arb_mpnet_relative_bucket(int32_t relative_position, int32_t num_buckets, in
  * scores[q, r] = <queries[q], corpus[id]>, rows ordered by (score desc, id asc);
  * out_ids = local row + id_offset (int64), unused slots (k > N) hold score -inf / id -1.
  * dtype ARB_DTYPE_BF16: operands bf16, scores accumulate bf16 products exactly in fp32.
- * dtype ARB_DTYPE_F32 : operands fp32, scored via a 3-term bf16 split and re-scored in fp32.
+ * dtype ARB_DTYPE_F32 : operands fp32, scored in one tf32 tensor-core pass over the stored rows; the
+ *                       k + 22 best are re-scored with exact fp32 FMAs and re-ranked (returned scores are
+ *                       true fp32 dot products). See arb_topk_search_f32 for the exactness verdict.
  * ------------------------------------------------------------------------------------------ */
 size_t arb_topk_search_workspace_bytes(int32_t dtype, int64_t Q, int64_t N, int32_t D, int32_t k);
 int arb_topk_search(const void* queries_dev, const void* corpus_dev, int32_t dtype, int64_t Q,
                     int64_t N, int32_t D, int32_t k, float* out_scores_dev, int64_t* out_ids_dev,
                     int64_t id_offset, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* fp32 search with its exactness verdict.
+ * mode 0: tf32 pass + exact re-score (what arb_topk_search does for ARB_DTYPE_F32). tf32 scoring is off by
+ *   at most 2^-9 |q| |c| for any row, so the result is provably the exact top-k whenever the exact k-th
+ *   best score clears the worst candidate's approximate score by that bound; unverified_dev[q] (int32 [Q],
+ *   may be NULL) receives 0 when it does, 1 when it does not (dense near-ties around rank k).
+ * mode 1: 3-term bf16 hi/lo split (scoring error ~4e-7) + exact re-score: 3x the tensor-core work and a
+ *   1.5x copy of the corpus in the workspace — the fallback for the queries mode 0 left unverified.
+ * corpus_max_norm: an upper bound of the corpus rows' L2 norms (1 for the unit rows of `encode`). */
+size_t arb_topk_search_f32_workspace_bytes(int64_t Q, int64_t N, int32_t D, int32_t k, int32_t mode);
+int arb_topk_search_f32(const float* queries_dev, const float* corpus_dev, int64_t Q, int64_t N, int32_t D, int32_t k,
+                        float corpus_max_norm, float* out_scores_dev, int64_t* out_ids_dev, int64_t id_offset,
+                        int32_t* unverified_dev, int32_t mode, void* workspace_dev, size_t workspace_bytes, void* stream);
 /* Merge G sorted per-shard lists (e.g. the all-gathered [G,Q,k] of a row-sharded corpus). */
 int arb_topk_merge(const float* scores_dev, const int64_t* ids_dev, int32_t G, int64_t Q, int32_t k,
                    float* out_scores_dev, int64_t* out_ids_dev, void* stream);

@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 import torch
 
+from arxiv_rag_b200 import _lib
 from arxiv_rag_b200 import search as S
 from oracle import search_oracle as so
 from tests.conftest import GOLDEN
@@ -311,3 +312,55 @@ def test_full_size_5m_corpus_properties(cuda):
         assert torch.equal(i1, fi) and torch.equal(s1, fs)
     finally:
         _lib.check(_lib.lib().arb_set_search_mode(0))
+
+
+def test_fp32_verdict_and_exact_fallback(cuda):
+    """fp32 corpus: one tf32 pass + exact re-score carries a per-query proof of exactness; queries
+    whose k-th best score does not clear the worst candidate by the tf32 error bound are re-run
+    through the split-bf16 path. Planted: 60 near-copies of one query (scores within 2e-4 of each
+    other, far more of them than the 32 candidates kept) — those queries cannot be verified and
+    must come back exact through the fallback; ordinary queries verify."""
+    rng = np.random.default_rng(3)
+    N, D, k = 20_000, 768, 10
+    c = so.synthetic_unit_rows(N, D, seed=0)
+    q = so.synthetic_unit_rows(8, D, seed=1)
+    for j in range(60):  # a dense cluster around query 0 and query 5
+        for qi, base in ((0, 1000), (5, 9000)):
+            v = q[qi] + 2e-3 * rng.standard_normal(D).astype(np.float32)
+            c[base + 7 * j] = v / np.linalg.norm(v)
+    idx = S.CorpusIndex(torch.from_numpy(c))
+    s, i = idx.search(torch.from_numpy(q), k)
+    rep = so.check_topk(s.cpu().numpy(), i.cpu().numpy(), q, c, k, tol=TOL)
+    assert rep["ok"], rep
+    assert 2 <= idx.fallback_queries <= 4, idx.fallback_queries  # the two clustered queries (a few more at most)
+    # the two modes of the C entry point, side by side
+    qd, cd = torch.from_numpy(q).cuda(), torch.from_numpy(c).cuda()
+    lib = _lib.lib()
+    outs = []
+    for mode in (0, 1):
+        need = lib.arb_topk_search_f32_workspace_bytes(8, N, D, k, mode)
+        ws = torch.empty(need, dtype=torch.uint8, device=cuda)
+        sc = torch.empty(8, k, device=cuda)
+        ids = torch.empty(8, k, dtype=torch.int64, device=cuda)
+        fl = torch.full((8,), -1, dtype=torch.int32, device=cuda)
+        _lib.check(lib.arb_topk_search_f32(qd.data_ptr(), cd.data_ptr(), 8, N, D, k, 1.0 + 1e-6, sc.data_ptr(), ids.data_ptr(), 0,
+                                           fl.data_ptr(), mode, ws.data_ptr(), ws.numel(), _lib.current_stream()))
+        outs.append((sc.cpu().numpy(), ids.cpu().numpy(), fl.cpu().numpy()))
+    assert outs[0][2][0] == 1 and outs[0][2][5] == 1 and outs[0][2][[1, 2, 3, 4, 6, 7]].sum() == 0  # verdicts of the tf32 pass
+    assert (outs[1][2] == 0).all()
+    assert so.check_topk(outs[1][0], outs[1][1], q, c, k, tol=TOL)["ok"]
+    ok_rows = [1, 2, 3, 4, 6, 7]  # verified rows of the tf32 pass are exact on their own
+    assert so.check_topk(outs[0][0][ok_rows], outs[0][1][ok_rows], q[ok_rows], c, k, tol=TOL)["ok"]
+
+
+def test_fp32_non_unit_rows(cuda):
+    """The verdict scales with |q| and the largest corpus row norm, so un-normalised rows work too."""
+    rng = np.random.default_rng(5)
+    c = (rng.standard_normal((5000, 256)) * rng.uniform(0.1, 7.0, (5000, 1))).astype(np.float32)
+    q = (rng.standard_normal((33, 256)) * 3.0).astype(np.float32)
+    idx = S.CorpusIndex(torch.from_numpy(c))
+    assert 6.0 < idx.max_norm < 200.0
+    s, i = idx.search(torch.from_numpy(q), 10)
+    ref_s, ref_i = so.oracle_search(q, c, 10)
+    assert (i.cpu().numpy() == ref_i).all()
+    assert np.abs(s.cpu().numpy() - ref_s).max() < 1e-3 * np.abs(ref_s).max()
