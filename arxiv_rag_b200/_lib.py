@@ -96,6 +96,7 @@ SIGNATURES = {
     "arb_ipc_import": (C.c_int, [_VP, C.POINTER(C.c_void_p)]),
     "arb_ipc_close": (C.c_int, [_VP]),
     "arb_topk_exchange_merge": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _I32, _SZ, _VP, _VP, _VP]),
+    "arb_topk_exchange_status": (C.c_int, [_VP]),
     "arb_topk_record_bytes": (_SZ, [_I64, _I32]),
     "arb_topk_record_ids_offset": (_SZ, [_I64, _I32]),
     "arb_topk_merge_records": (C.c_int, [_VP, _I32, _I64, _I32, _VP, _VP, _VP]),

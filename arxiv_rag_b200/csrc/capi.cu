@@ -549,6 +549,8 @@ int arb_topk_exchange_merge(const void* local_record_dev, const void* peer_bufs_
                                       slot_bytes, out_scores_dev, out_ids_dev, static_cast<cudaStream_t>(stream));
 }
 
+int arb_topk_exchange_status(const void* own_buf_dev) { return topk_exchange_status(own_buf_dev); }
+
 int arb_set_search_mode(int32_t mode) {
     ARB_REQUIRE(mode >= 0 && mode <= 2, "search mode %d must be 0 (auto), 1 (single CTA) or 2 (CTA pairs)", mode);
     set_search_mode(mode);

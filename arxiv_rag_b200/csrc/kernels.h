@@ -108,6 +108,7 @@ int launch_topk_merge_records(const void* records, int G, int64_t Q, int k, floa
                               int64_t* out_ids, cudaStream_t stream);
 // Peer-memory exchange (one kernel: push records to all ranks' mapped buffers, flag, wait, merge).
 size_t topk_exchange_bytes(int G, size_t slot_bytes);
+int topk_exchange_status(const void* own_buf_dev);
 int launch_topk_exchange_merge(const void* local_record, void* const* peer_bufs_dev, int rank, int G, int64_t Q,
                                int k, size_t slot_bytes, float* out_scores, int64_t* out_ids, cudaStream_t stream);
 

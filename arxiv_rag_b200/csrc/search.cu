@@ -13,6 +13,8 @@
 // registers, each thread folds its own buffer; k <= 128: lists in shared memory, merged by the
 // whole warp one row at a time). Per-item lists go to the workspace and a k-way merge kernel
 // produces the final order.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tmap.cuh"
@@ -623,7 +625,13 @@ struct ExchangeHeader {
     uint32_t flags[2][kExchMaxRanks];
     uint32_t done;
     uint32_t epoch;
+    uint32_t error;  // sticky: 1 + the first peer whose record did not arrive within the timeout
 };
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
@@ -637,7 +645,7 @@ __device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
 __global__ void __launch_bounds__(kMergeThreads)
 topk_exchange_merge_kernel(const uint8_t* __restrict__ local_record, uint8_t* const* __restrict__ peer_bufs, int rank,
                            int G, int64_t Q, int k, size_t rec_bytes, size_t ids_off, size_t slot_bytes,
-                           float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+                           float* __restrict__ out_scores, int64_t* __restrict__ out_ids, uint64_t timeout_ns) {
     extern __shared__ __align__(16) uint8_t s_merge[];
     const int tid = threadIdx.x;
     uint8_t* mine_raw = peer_bufs[rank];
@@ -666,12 +674,34 @@ topk_exchange_merge_kernel(const uint8_t* __restrict__ local_record, uint8_t* co
                 st_relaxed_sys(&reinterpret_cast<ExchangeHeader*>(peer_bufs[p])->flags[parity][rank], epoch);
         }
     }
-    // (c) all records of this epoch have landed in my buffer
+    // (c) all records of this epoch have landed in my buffer. The wait is bounded: a peer that died
+    // (or never made the call) must not hang this rank's stream forever. On a timeout the kernel
+    // records the missing peer in the header (sticky, read by arb_topk_exchange_status), returns
+    // "no result" rows (-inf / -1) and later calls return at once.
+    int lost = 0;
     if (tid < G) {
-        while (ld_acquire_sys(&mine->flags[parity][tid]) != epoch) {
+        if (ld_acquire_sys(&mine->error) != 0u) {
+            lost = 1;
+        } else {
+            const uint64_t t0 = global_timer_ns();
+            uint32_t polls = 0;
+            while (ld_acquire_sys(&mine->flags[parity][tid]) != epoch) {
+                if ((++polls & 1023u) == 0u && global_timer_ns() - t0 > timeout_ns) {
+                    atomicCAS(&mine->error, 0u, 1u + static_cast<uint32_t>(tid));
+                    lost = 1;
+                    break;
+                }
+            }
         }
     }
-    __syncthreads();
+    if (__syncthreads_or(lost)) {
+        for (int64_t q = blockIdx.x; q < Q; q += gridDim.x)
+            for (int j = tid; j < k; j += kMergeThreads) {
+                out_scores[q * k + j] = -INFINITY;
+                out_ids[q * k + j] = -1;
+            }
+        return;
+    }
     // (d) merge them
     const uint8_t* base = mine_raw + kExchHeaderBytes + parity * G * slot_bytes;
     for (int64_t q = blockIdx.x; q < Q; q += gridDim.x) {
@@ -787,6 +817,19 @@ int launch_topk_merge_records(const void* records, int G, int64_t Q, int k, floa
 
 size_t topk_exchange_bytes(int G, size_t slot_bytes) { return kExchHeaderBytes + 2 * static_cast<size_t>(G) * slot_bytes; }
 
+// Host read of the sticky error word of this rank's exchange buffer (synchronises the device).
+int topk_exchange_status(const void* own_buf_dev) {
+    ARB_REQUIRE(own_buf_dev != nullptr, "topk_exchange_status: null buffer");
+    ExchangeHeader h;
+    ARB_CHECK_CUDA(cudaMemcpy(&h, own_buf_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h.error != 0u) {
+        set_error("topk_exchange_merge: the record of rank %u did not arrive within the timeout (ARB_EXCHANGE_TIMEOUT_MS); "
+                  "results since then are empty — rebuild the exchange", h.error - 1u);
+        return ARB_ERR_CUDA;
+    }
+    return ARB_OK;
+}
+
 int launch_topk_exchange_merge(const void* local_record, void* const* peer_bufs_dev, int rank, int G, int64_t Q,
                                int k, size_t slot_bytes, float* out_scores, int64_t* out_ids, cudaStream_t stream) {
     ARB_REQUIRE(local_record && peer_bufs_dev && out_scores && out_ids, "topk_exchange_merge: null pointer");
@@ -807,9 +850,14 @@ int launch_topk_exchange_merge(const void* local_record, void* const* peer_bufs_
         ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     // every block spins on the flags, so all of them must be resident at once: at most one per SM
     const int grid = static_cast<int>(Q < num_sms() ? Q : num_sms());
+    static const uint64_t timeout_ns = []() {
+        const char* e = getenv("ARB_EXCHANGE_TIMEOUT_MS");
+        const long ms = e ? atol(e) : 10000;
+        return static_cast<uint64_t>(ms > 0 ? ms : 10000) * 1000000ull;
+    }();
     kern<<<grid, kMergeThreads, smem, stream>>>(static_cast<const uint8_t*>(local_record),
                                                 reinterpret_cast<uint8_t* const*>(peer_bufs_dev), rank, G, Q, k, rec,
-                                                topk_record_ids_offset(Q, k), slot_bytes, out_scores, out_ids);
+                                                topk_record_ids_offset(Q, k), slot_bytes, out_scores, out_ids, timeout_ns);
     ARB_CHECK_CUDA(cudaGetLastError());
     return ARB_OK;
 }

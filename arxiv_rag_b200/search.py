@@ -272,6 +272,13 @@ class ShardedCorpusIndex:
                     lib.arb_exchange_free(own)
             dist.barrier(group=self.group)
 
+    def check_exchange(self) -> None:
+        """Raise if the peer-memory exchange lost a rank (its bounded wait timed out) since the index
+        was built. Synchronises the device; call it after a search whose result looks empty (-1 ids)."""
+        if self._exch is not None:
+            with self.index._torch.cuda.device(self.index.corpus.device):
+                _lib.check(_lib.lib().arb_topk_exchange_status(self._exch[0]))
+
     @property
     def exchange(self) -> str:
         return "peer-memory kernel (CUDA IPC over NVLink)" if self._exch is not None else "nccl all_gather"

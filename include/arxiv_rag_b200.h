@@ -183,6 +183,11 @@ int arb_ipc_import(const void* handle_64, void** dev_ptr_out);
 int arb_ipc_close(void* dev_ptr);
 int arb_topk_exchange_merge(const void* local_record_dev, const void* peer_bufs_dev, int32_t rank, int32_t G, int64_t Q,
                             int32_t k, size_t slot_bytes, float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+/* The exchange kernel waits for its peers' records for at most ARB_EXCHANGE_TIMEOUT_MS (default 10 s).
+ * If a record never arrives (a rank died or skipped the call) it returns -inf / -1 rows and marks this
+ * rank's buffer; this call (which synchronises the device) then returns ARB_ERR_CUDA with the peer's
+ * rank in arb_last_error(). ARB_OK otherwise. */
+int arb_topk_exchange_status(const void* own_buf_dev);
 /* out[i] = cos(emb[i], emb[i-1]) for fp32 rows [n, D] (out[0] = 1): the adjacent-sentence similarity
  * TextChunker._chunk_semantic computes with _cosine_similarity (text_processor.py:1547-1561, :1601-1605). */
 int arb_adjacent_cosine(const float* emb_dev, int64_t n, int32_t D, float* out_dev, void* stream);

@@ -71,6 +71,23 @@ def main():
     t_local = timed(lambda: ref_index.search(q, 10))
     t_peer = timed(lambda: peer.search_graphed(q, 10))
     t_nccl = timed(lambda: nccl.search_graphed(q, 10))
+    # A lost rank: rank 0 makes one exchange call that its peers skip. Its bounded wait (ARB_EXCHANGE_TIMEOUT_MS,
+    # set to 300 ms for this check by the caller) must give up, return empty rows and mark the buffer
+    # instead of hanging the stream. (Last check: the exchange is unusable afterwards by design.)
+    lost_ok = True
+    if os.environ.get("CHECK_LOST_RANK") == "1" and peer._exch is not None:
+        dist.barrier()
+        if rank == 0:
+            ps, pi = peer.search(q, 10)
+            torch.cuda.synchronize()
+            try:
+                peer.check_exchange()
+                lost_ok = False
+            except Exception as e:  # noqa: BLE001
+                lost_ok = "did not arrive" in str(e) and bool((pi == -1).all())
+            print(f"[{'PASS' if lost_ok else 'FAIL'}] lost rank: bounded wait gave up, rows empty, status reports the peer", flush=True)
+        dist.barrier()
+        ok_all &= lost_ok
     if rank == 0:
         print(f"Q=64 k=10 shard {hi - lo} rows (graph replay): peer exchange {t_peer * 1e3:.1f} us, nccl all_gather {t_nccl * 1e3:.1f} us; "
               f"unsharded {N}-row search eager {t_local * 1e3:.1f} us", flush=True)
