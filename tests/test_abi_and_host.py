@@ -342,3 +342,42 @@ def test_reference_process_pool_restatement_matches_in_process():
         assert float(out.stdout.split("MAXDIFF")[1]) < 1e-6
     finally:
         os.unlink(path)
+
+
+def test_gpu_collection_persist_and_reload(tmp_path):
+    """vector_store.GpuCollection: the store `store_in_chroma_batched` (:323-468) fills, as plain
+    files. Same id / document / metadata rules, shards of `shard_rows`, manifest lists only complete
+    shards, bf16 rows round to nearest even, a reopened collection sees the same records."""
+    import torch
+
+    from arxiv_rag_b200 import vector_store as vs
+
+    rng = np.random.default_rng(1)
+    emb = rng.standard_normal((23, 16)).astype(np.float32)
+    chunks = _chunks(23)
+    del chunks[7]["chunk_id"]
+    chunks[9]["metadata"].pop("section")
+    col = vs.store_in_gpu_index_batched(chunks, list(emb) + [emb[0]], str(tmp_path), "papers", batch_size=5)  # one embedding too many
+    assert col.count() == 23
+    col2 = vs.GpuCollection(str(tmp_path), "papers")
+    assert col2.count() == 23 and col2.manifest["dim"] == 16 and col2.manifest["dtype"] == "bf16"
+    assert col2.ids[7] == "chunk_7" and col2.ids[8] == chunks[8]["chunk_id"]
+    assert col2.documents[3] == chunks[3]["text"]
+    assert col2.metadatas[9] == {"paper_id": "2101.00009", "section": "unknown", "quality_score": pytest.approx(0.909), "chunk_index": "9"}
+    bits = col2.load_rows(5, 12)
+    assert bits.dtype == np.uint16 and bits.shape == (7, 16)
+    want = torch.from_numpy(emb[5:12]).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    assert np.array_equal(bits, want)
+    # small shards + append after reopen
+    col3 = vs.GpuCollection(str(tmp_path), "small", dtype="float32", shard_rows=10)
+    col3.add(ids=[f"a{i}" for i in range(23)], embeddings=emb)
+    assert len(col3.manifest["shards"]) == 2 and col3.manifest["total"] == 20 and col3.count() == 23
+    col3.persist()
+    col4 = vs.GpuCollection(str(tmp_path), "small")
+    assert [s["rows"] for s in col4.manifest["shards"]] == [10, 10, 3]
+    assert np.array_equal(col4.load_rows(8, 22), emb[8:22])
+    col4.add(ids=["z"], embeddings=emb[:1], documents=["doc"], metadatas=[{"k": 1}])
+    col4.persist()
+    assert vs.GpuCollection(str(tmp_path), "small").ids[-1] == "z"
+    with pytest.raises(ValueError):
+        col4.add(ids=["bad"], embeddings=np.zeros((1, 8), np.float32))

@@ -364,3 +364,19 @@ def test_fp32_non_unit_rows(cuda):
     ref_s, ref_i = so.oracle_search(q, c, 10)
     assert (i.cpu().numpy() == ref_i).all()
     assert np.abs(s.cpu().numpy() - ref_s).max() < 1e-3 * np.abs(ref_s).max()
+
+
+def test_gpu_collection_query(cuda, tmp_path):
+    """The persisted GPU index answers Chroma-shaped queries with the exact top-k of its rows."""
+    from arxiv_rag_b200 import vector_store as vs
+
+    c = so.synthetic_unit_rows(3000, 768, seed=0, bf16=True)
+    chunks = [{"chunk_id": f"c{i}", "text": f"text {i}", "metadata": {"paper_id": i // 10, "quality_score": 0.9}} for i in range(3000)]
+    vs.store_in_gpu_index_batched(chunks, list(c), str(tmp_path), "papers", batch_size=700)
+    col = vs.GpuCollection(str(tmp_path), "papers")
+    q = so.synthetic_unit_rows(5, 768, seed=1, bf16=True)
+    res = col.query(q, n_results=4)
+    ref_s, ref_i = so.oracle_search(q, c, 4)
+    assert res["ids"] == [[f"c{j}" for j in row] for row in ref_i]
+    assert np.allclose(np.array(res["scores"]), ref_s, atol=1e-6) and np.allclose(np.array(res["distances"]), 1 - ref_s, atol=1e-6)
+    assert res["documents"][2][0] == f"text {ref_i[2, 0]}" and res["metadatas"][0][1]["paper_id"] == str(ref_i[0, 1] // 10)
