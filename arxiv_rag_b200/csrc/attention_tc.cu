@@ -493,7 +493,7 @@ int launch_attention_tc(const h16* qkv, const float* rel_bias, int max_rel, cons
     }();
     auto kern = fp16 ? (defer ? attention_tc_kernel<true, true> : attention_tc_kernel<true, false>)
                      : (defer ? attention_tc_kernel<false, true> : attention_tc_kernel<false, false>);
-    ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ARB_CHECK_CUDA(set_max_smem_once(kern, smem));
     int ngroups = num_sms() / heads;
     if (ngroups < 1) ngroups = 1;
     if (ngroups > B) ngroups = B;

@@ -492,7 +492,7 @@ int launch_attention_tc2(const h16* qkv, const float* rel_bias, int max_rel, con
         return ARB_ERR_CUDA;
     }
     auto kern = fp16 ? attention_tc2_kernel<true> : attention_tc2_kernel<false>;
-    ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ARB_CHECK_CUDA(set_max_smem_once(kern, smem));
     int ngroups = num_sms() / heads;
     if (ngroups < 1) ngroups = 1;
     if (ngroups > B) ngroups = B;

@@ -29,6 +29,26 @@ const char* get_error();
         }                                    \
     } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel, device and size instead of on
+// every launch (the attribute is sticky; the encoder launches 63 kernels per forward).
+template <class Kern>
+inline cudaError_t set_max_smem_once(Kern kern, int bytes) {
+    struct Slot { const void* fn; int dev; int bytes; };
+    static thread_local Slot cache[64];
+    static thread_local int used = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const void* fn = reinterpret_cast<const void*>(kern);
+    for (int i = 0; i < used; ++i)
+        if (cache[i].fn == fn && cache[i].dev == dev && cache[i].bytes >= bytes) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) {
+        if (used == 64) used = 0;
+        cache[used++] = Slot{fn, dev, bytes};
+    }
+    return e;
+}
+
 inline int num_sms() {
     static int n = 0;
     if (!n) {

@@ -506,7 +506,7 @@ static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb
                 smem = Gemm2ColSmem::kExtraOffset + 1024;
             }
         }
-        ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ARB_CHECK_CUDA(set_max_smem_once(kern, smem));
         const int64_t tiles = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kGemmBN - 1) / kGemmBN);
         int64_t nclusters = num_sms() / 2;
         if (nclusters > tiles) nclusters = tiles;
@@ -528,7 +528,7 @@ static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb
     auto kern = gemm16_kernel<EPI, kF16, OutT, false>;
     constexpr int smem = GemmSmem::kExtraOffset + 1024;  // +1024: alignment slack
     static_assert(smem <= 232448, "GEMM shared memory exceeds 227 KB");
-    ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ARB_CHECK_CUDA(set_max_smem_once(kern, smem));
     const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + kGemmBN - 1) / kGemmBN);
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, tc, tr, bias, M, N, K, fold, umma_idesc_16bit(kBM, kGemmBN, kF16));

@@ -774,7 +774,7 @@ static int launch_merge_impl(const float* scores, const IdT* ids, int G, int64_t
         ARB_REQUIRE(Q < (1ll << 31), "topk_merge: Q too large");
         auto kern = topk_tree_merge_kernel<IdT>;
         if (tree > 48 * 1024)
-            ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tree)));
+            ARB_CHECK_CUDA(set_max_smem_once(kern, static_cast<int>(tree)));
         kern<<<static_cast<int>(Q), kMergeThreads, tree, stream>>>(scores, ids, G, stride_s, stride_i, Q, k, id_offset,
                                                                    out_scores, out_ids);
     } else {
@@ -847,7 +847,7 @@ int launch_topk_exchange_merge(const void* local_record, void* const* peer_bufs_
     }
     auto kern = topk_exchange_merge_kernel;
     if (smem > 48 * 1024)
-        ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        ARB_CHECK_CUDA(set_max_smem_once(kern, static_cast<int>(smem)));
     // every block spins on the flags, so all of them must be resident at once: at most one per SM
     const int grid = static_cast<int>(Q < num_sms() ? Q : num_sms());
     static const uint64_t timeout_ns = []() {
@@ -939,7 +939,7 @@ static int launch_search_16(const uint16_t* q, const uint16_t* corpus, int64_t Q
     auto launch = [&](auto kern, int ring_bytes, int lk, int cbuf) -> int {
         const int slots = lk + (cbuf > 1 ? cbuf + 1 : cbuf);
         const int smem = ring_bytes + slots * kBM * 8 + 1024;
-        ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ARB_CHECK_CUDA(set_max_smem_once(kern, smem));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(static_cast<unsigned>(p.grid));
         cfg.blockDim = dim3(kSearchThreads);
