@@ -101,6 +101,9 @@ SIGNATURES = {
     "arb_topk_record_ids_offset": (_SZ, [_I64, _I32]),
     "arb_topk_merge_records": (C.c_int, [_VP, _I32, _I64, _I32, _VP, _VP, _VP]),
     "arb_adjacent_cosine": (C.c_int, [_VP, _I64, _I32, _VP, _VP]),
+    "arb_tokenizer_create": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, C.POINTER(C.c_void_p)]),
+    "arb_tokenizer_destroy": (C.c_int, [_VP]),
+    "arb_tokenizer_encode": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _I32, _VP, _I64, _VP, _VP]),
     "arb_gemm16": (C.c_int, [_VP, _I64, _VP, _I64, _VP, _I64, _VP, _VP, _I64, _I64, _I32, _I32, _I32, _I32, _VP]),
     "arb_gemm16_f32out": (C.c_int, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP]),
     "arb_embed_layernorm": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F, _I32, _VP]),

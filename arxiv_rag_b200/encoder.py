@@ -40,8 +40,8 @@ class B200SentenceEncoder:
         exists offline.
     tokenizer : optional callable `tokenizer(list[str], padding=True, truncation=True,
         max_length=..., return_tensors='np') -> {'input_ids', 'attention_mask'}` — a HF tokenizer or
-        the in-tree `tokenizer.WordPieceTokenizer`. `vocab_file=...` builds the in-tree one from the
-        model's `vocab.txt`. Without either, `encode` accepts pre-tokenised `(input_ids, attention_mask)`
+        the in-tree `tokenizer.WordPieceTokenizer`. `vocab_file=...` builds the in-tree native one
+        (`tokenizer.NativeWordPieceTokenizer`, C-ABI `arb_tokenizer_*`) from the model's `vocab.txt`. Without either, `encode` accepts pre-tokenised `(input_ids, attention_mask)`
         only (no vocabulary ships offline).
     max_batch / max_seq : capacity of the activation workspace (tokens = max_batch * max_seq).
     dtype : 16-bit format of weights, activations and tensor-core operands (fp32 accumulation and
@@ -76,10 +76,10 @@ class B200SentenceEncoder:
         self.max_batch = int(max_batch)
         self.max_seq_length = min(arch.max_seq_length, self.max_seq)
         if tokenizer is None and vocab_file is not None:
-            from .tokenizer import WordPieceTokenizer
+            from .tokenizer import NativeWordPieceTokenizer
 
-            tokenizer = WordPieceTokenizer(vocab_file, kind="bert" if arch.kind == "bert" else "mpnet",
-                                           max_length=self.max_seq_length)
+            tokenizer = NativeWordPieceTokenizer(vocab_file, kind="bert" if arch.kind == "bert" else "mpnet",
+                                                 max_length=self.max_seq_length)
         self.tokenizer = tokenizer
         if state_dict is None:
             state_dict = synthetic_state_dict(arch, seed)

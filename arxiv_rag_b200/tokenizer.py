@@ -18,6 +18,12 @@ transformers `MPNetTokenizer` / `BertTokenizer`):
 
 `tokenize_batch` returns padded int32 `input_ids` / `attention_mask` arrays, like
 `tokenizer(texts, padding=True, truncation=True, max_length=..., return_tensors='np')`.
+
+`WordPieceTokenizer` is the pure-Python statement of those steps (~0.5k chunks/s per thread).
+`NativeWordPieceTokenizer` runs the same steps in the C-ABI library (`arb_tokenizer_*`,
+csrc/tokenizer.cu: multi-threaded, no GIL) and hands the rare rows whose normalisation depends on
+context (U+03A3, non-Mn combining marks, lone surrogates) back to the Python class, so the two
+return identical arrays; it is what `B200SentenceEncoder(vocab_file=...)` uses.
 """
 from __future__ import annotations
 
@@ -164,6 +170,66 @@ class WordPieceTokenizer:
             texts = [texts]
         ids, mask = self.tokenize_batch(list(texts), max_length if truncation else 1 << 30)
         return {"input_ids": ids, "attention_mask": mask}
+
+
+class NativeWordPieceTokenizer(WordPieceTokenizer):
+    """Same constructor and results as `WordPieceTokenizer`; `tokenize_batch` runs in the library.
+    num_threads: worker threads per call (default: min(16, cores))."""
+
+    def __init__(self, vocab, kind: str = "mpnet", do_lower_case: bool = True, max_length: int = 384,
+                 num_threads: int | None = None):
+        super().__init__(vocab, kind, do_lower_case, max_length)
+        import ctypes as C
+        import os
+
+        from . import _lib
+
+        self._libmod, self._C = _lib, C
+        self.num_threads = int(num_threads) if num_threads else min(16, os.cpu_count() or 1)
+        toks = [t.encode("utf-8", "surrogatepass") for t in self.vocab]
+        offs = np.zeros(len(toks) + 1, np.int64)
+        np.cumsum([len(t) for t in toks], out=offs[1:])
+        ids = np.fromiter(self.vocab.values(), np.int32, len(toks))
+        blob = b"".join(toks)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().arb_tokenizer_create(blob, offs.ctypes.data, ids.ctypes.data, len(toks), self.cls_id,
+                                                   self.sep_id, self.pad_id, self.unk_id, int(do_lower_case), C.byref(h)))
+        self._handle = h
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            try:
+                self._libmod.lib().arb_tokenizer_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    def tokenize_batch(self, texts: Sequence[str], max_length: int | None = None):
+        max_length = self.max_length if max_length is None else int(max_length)
+        n = len(texts)
+        if n == 0:
+            return np.full((0, 1), self.pad_id, np.int32), np.zeros((0, 1), np.int32)
+        if max_length > 1 << 20:  # "no truncation": the row buffer is sized from the text instead
+            max_length = max(len(t) for t in texts) + 2
+        raw = [t.encode("utf-8", "surrogatepass") for t in texts]
+        offs = np.zeros(n + 1, np.int64)
+        np.cumsum([len(b) for b in raw], out=offs[1:])
+        stride = max(max_length, 2)
+        ids = np.empty((n, stride), np.int32)
+        lens = np.empty(n, np.int32)
+        fb = np.empty(n, np.uint8)
+        self._libmod.check(self._libmod.lib().arb_tokenizer_encode(
+            self._handle, b"".join(raw), offs.ctypes.data, n, max_length, self.num_threads, ids.ctypes.data, stride,
+            lens.ctypes.data, fb.ctypes.data))
+        for r in np.flatnonzero(fb):  # context-dependent rows: the Python statement of the same steps
+            row = self.encode(texts[r], max_length)
+            ids[r, :len(row)] = row
+            ids[r, len(row):] = self.pad_id
+            lens[r] = len(row)
+        S = int(lens.max())
+        mask = (np.arange(S, dtype=np.int32)[None, :] < lens[:, None]).astype(np.int32)
+        return np.ascontiguousarray(ids[:, :S]), mask
 
 
 def text_lengths(texts: Iterable[str]) -> np.ndarray:

@@ -191,6 +191,28 @@ int arb_topk_exchange_status(const void* own_buf_dev);
 /* out[i] = cos(emb[i], emb[i-1]) for fp32 rows [n, D] (out[0] = 1): the adjacent-sentence similarity
  * TextChunker._chunk_semantic computes with _cosine_similarity (text_processor.py:1547-1561, :1601-1605). */
 int arb_adjacent_cosine(const float* emb_dev, int64_t n, int32_t D, float* out_dev, void* stream);
+/* ------------------------------------------------------------------------------------------
+ * Host-side WordPiece tokenizer (no GPU work): the string half of SentenceTransformer.encode
+ * (generate_embeddings_parallel.py:146-153 hands List[str] to model.encode; the tokenizer that
+ * sentence-transformers calls first is BertNormalizer + BertPreTokenizer + WordPiece + the
+ * <s>..</s> / [CLS]..[SEP] template). Specification and checker: arxiv_rag_b200/tokenizer.py.
+ *
+ * create : the vocabulary as UTF-8 token bytes (token i = bytes[offsets[i], offsets[i+1])) with its
+ *          ids; a repeated token keeps the last id.
+ * encode : n UTF-8 texts (text r = bytes[offsets[r], offsets[r+1])) -> out_ids[r, 0..out_lens[r])
+ *          = cls, pieces (at most max_length-2), sep; the rest of the row (out_stride >=
+ *          max(max_length, 2) int32) is pad. Rows whose normalisation depends on context
+ *          (U+03A3, the 26 non-Mn combining marks with a non-zero class) or that are not valid
+ *          UTF-8 get out_fallback[r] = 1 and must be re-done by the caller (the Python class does).
+ *          num_threads <= 0: all hardware threads. Thread-safe: a handle is read-only after create. */
+int arb_tokenizer_create(const char* token_bytes, const int64_t* token_offsets, const int32_t* token_ids, int32_t n_tokens,
+                         int32_t cls_id, int32_t sep_id, int32_t pad_id, int32_t unk_id, int32_t do_lower_case,
+                         void** handle_out);
+int arb_tokenizer_destroy(void* handle);
+int arb_tokenizer_encode(void* handle, const char* text_bytes, const int64_t* text_offsets, int64_t n_texts,
+                         int32_t max_length, int32_t num_threads, int32_t* out_ids, int64_t out_stride,
+                         int32_t* out_lens, uint8_t* out_fallback);
+
 /* Upper bound on the kernel launches one arb_topk_search call enqueues (the query pad copy is skipped
  * when Q is a whole number of query tiles). */
 int arb_topk_search_launches(int32_t dtype);
