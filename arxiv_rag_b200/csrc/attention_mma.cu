@@ -100,6 +100,8 @@ attention_kernel(const h16* __restrict__ qkv, const float* __restrict__ rel_bias
     const h16* base = qkv + static_cast<int64_t>(b) * S * ld;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+    pdl_launch_dependents();
+    pdl_wait();
     // ---- stage K, V (zero rows beyond S), bias table and mask
     if (tid == 0) s_last = -1;
     if (tid < 16) s_blk_clear[tid] = 1;
@@ -293,9 +295,8 @@ int launch_attention_mma(const h16* qkv, const float* rel_bias, int max_rel, con
     ARB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
     const float scale_log2e = kLog2e / sqrtf(static_cast<float>(dh));
-    kern<<<dim3(heads, B), kAttnThreads, smem, stream>>>(qkv, rel_bias, max_rel, mask, ctx, S, heads,
-                                                         scale_log2e);
-    ARB_CHECK_CUDA(cudaGetLastError());
+    ARB_CHECK_CUDA(launch_kernel(kern, dim3(heads, B), dim3(kAttnThreads), smem, stream, 1, qkv, rel_bias, max_rel, mask, ctx, S,
+                                 heads, scale_log2e));
     return ARB_OK;
 }
 

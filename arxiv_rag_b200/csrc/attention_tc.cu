@@ -258,6 +258,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // the bias table, barriers and TMEM above depend on nothing an earlier kernel wrote; qkv and mask do
+    pdl_launch_dependents();
+    pdl_wait();
     float bmax = red[0], bmin = red[16];
 #pragma unroll
     for (int w = 1; w < kAtThreads / 32; ++w) {
@@ -499,8 +502,8 @@ int launch_attention_tc(const h16* qkv, const float* rel_bias, int max_rel, cons
     if (ngroups > B) ngroups = B;
     const int grid = ngroups * heads;
     const float scale_log2e = kAtLog2e / sqrtf(static_cast<float>(dh));
-    kern<<<grid, kAtThreads, smem, stream>>>(tq, tkv, rel_bias, max_rel, mask, ctx, B, S, heads, Kh, scale_log2e);
-    ARB_CHECK_CUDA(cudaGetLastError());
+    ARB_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(kAtThreads), smem, stream, 1, tq, tkv, rel_bias, max_rel, mask, ctx, B, S,
+                                 heads, Kh, scale_log2e));
     return ARB_OK;
 }
 

@@ -244,6 +244,8 @@ static int mpnet_build_layers(Mpnet* m, const ArbMpnetWeights* w, std::vector<La
 
 constexpr int kShortSeq = 32;
 
+constexpr int64_t kPdlMaxTokens = 16384;
+
 static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B, int S, float* out,
                         cudaStream_t st) {
     const ArbMpnetConfig& c = m->cfg;
@@ -253,6 +255,14 @@ static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B
     const bool a16 = m->fp16 || use_f16_copy;
     const bool fmt = a16;  // one 16-bit format for every operand of this call
     const std::vector<LayerDev>& layers = use_f16_copy ? m->layers_f16 : m->layers;
+    // Query-time batches: the forward is 63 short kernels; launch them programmatically dependent so
+    // each one's set-up and weight prefetch overlap its predecessor (common.cuh: pdl_scope).
+    // ARB_PDL=0 never, 2 always, default: up to kPdlMaxTokens tokens.
+    static const int pdl_mode = []() {
+        const char* e = getenv("ARB_PDL");
+        return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 1;
+    }();
+    pdl_scope pdl(pdl_mode == 2 || (pdl_mode == 1 && T <= kPdlMaxTokens));
     int rc;
     if ((rc = launch_embed_ln(ids, m->word_emb, m->pos_emb, m->emb_g, m->emb_b, m->h, B, S, H,
                               c.vocab_size, c.max_position_embeddings, c.pad_token_id, c.position_mode,

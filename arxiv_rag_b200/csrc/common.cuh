@@ -49,6 +49,50 @@ inline cudaError_t set_max_smem_once(Kern kern, int bytes) {
     return e;
 }
 
+// Programmatic dependent launch for the encoder's kernel chain. While `pdl_scope` is alive on this
+// thread, `launch_kernel` adds cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel
+// may start (set-up, TMEM allocation, weight prefetch into L2) while its predecessor is still running,
+// and blocks in `griddepcontrol.wait` (ptx.cuh: pdl_wait) before it touches anything the predecessor
+// wrote. Every kernel launched this way executes pdl_wait on all threads, so completion stays
+// transitive along the chain. Used for small token counts (query-time latency), where the forward is
+// 63 short kernels and launch + set-up are a third of each.
+inline bool& pdl_flag() {
+    static thread_local bool on = false;
+    return on;
+}
+struct pdl_scope {
+    bool prev;
+    explicit pdl_scope(bool on) : prev(pdl_flag()) { pdl_flag() = on; }
+    ~pdl_scope() { pdl_flag() = prev; }
+};
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 unsigned cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    unsigned n = 0;
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster_x;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_flag()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 inline int num_sms() {
     static int n = 0;
     if (!n) {

@@ -201,6 +201,21 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     if constexpr (k2Cta) tmem_base = pipe2_setup(sm, warp, &tmap_a, &tmap_b, 2 * kEpiWarps);
     else tmem_base = pipe_setup(sm, warp, &tmap_a, &tmap_b, kEpiThreads);
 
+    // Programmatic dependent launch (small token counts): everything above ran while the previous
+    // kernel of the chain was still busy; so does the L2 prefetch of this CTA's first weight tile
+    // (B is never written by the chain). Activations, statistics and outputs only after pdl_wait.
+    pdl_launch_dependents();
+    if (warp == 2) {
+        Iter peek = it;
+        int row_a, row_b;
+        if (peek.next(row_a, row_b)) {
+            const int rb = row_b + (k2Cta ? rank * (BN / 2) : 0);
+            if (rb < N)
+                for (int kb = lane; kb < kblocks; kb += 32) tma_prefetch_2d(&tmap_b, kb * kBK, rb);
+        }
+    }
+    pdl_wait();
+
     if (warp == 0) {
         if (elect_one()) {
             if constexpr (k2Cta) pipe2_produce(sm, &tmap_a, &tmap_b, it, kblocks, rank, kEvictNormal, kEvictLast);
@@ -510,19 +525,8 @@ static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb
         const int64_t tiles = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kGemmBN - 1) / kGemmBN);
         int64_t nclusters = num_sms() / 2;
         if (nclusters > tiles) nclusters = tiles;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(static_cast<unsigned>(nclusters * 2));
-        cfg.blockDim = dim3(kGemmThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        ARB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tr, bias, M, N, K, fold, umma_idesc_16bit(2 * kBM, kGemmBN, kF16)));
+        ARB_CHECK_CUDA(launch_kernel(kern, dim3(static_cast<unsigned>(nclusters * 2)), dim3(kGemmThreads), smem, stream, 2, ta, tb,
+                                     tc, tr, bias, M, N, K, fold, umma_idesc_16bit(2 * kBM, kGemmBN, kF16)));
         return ARB_OK;
     }
     auto kern = gemm16_kernel<EPI, kF16, OutT, false>;
@@ -531,8 +535,8 @@ static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb
     ARB_CHECK_CUDA(set_max_smem_once(kern, smem));
     const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + kGemmBN - 1) / kGemmBN);
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, tc, tr, bias, M, N, K, fold, umma_idesc_16bit(kBM, kGemmBN, kF16));
-    ARB_CHECK_CUDA(cudaGetLastError());
+    ARB_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), smem, stream, 1, ta, tb, tc, tr, bias, M, N, K, fold,
+                                 umma_idesc_16bit(kBM, kGemmBN, kF16)));
     return ARB_OK;
 }
 

@@ -137,9 +137,24 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// pdl_wait: block until the grid this one was launched behind (common.cuh: launch_kernel under a
+// pdl_scope) has completed and its writes are visible; a no-op in an ordinary launch. Everything
+// before it may only touch memory no earlier kernel of the chain writes (weights, descriptors).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// pdl_launch_dependents: this CTA no longer minds the next grid starting. Issued AFTER a kernel's own
+// TMEM allocation, so an early dependent CTA can never take the columns its predecessor still needs.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
+}
+// Pull one box of a 2D tensor map into L2 (no shared-memory destination, no barrier).
+__device__ __forceinline__ void tma_prefetch_2d(const void* desc, int32_t x, int32_t y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(desc)),
+                 "r"(x), "r"(y)
+                 : "memory");
 }
 // L2 cache-policy constants (the encodings CUTLASS uses for TMA::CacheHintSm90).
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;

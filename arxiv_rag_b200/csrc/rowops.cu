@@ -57,6 +57,8 @@ embed_ln_kernel(const int32_t* __restrict__ ids, const float* __restrict__ word_
                 const float* __restrict__ pos_emb, const float* __restrict__ gamma,
                 const float* __restrict__ beta, h16* __restrict__ out, int S, int H,
                 int vocab, int max_pos, int pad_id, int pos_mode, float eps, int* __restrict__ err_flag) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ int smem_i[];
     int* s_pos = smem_i;              // [S] position id of each token
     int* s_chunk = smem_i + S;        // [ceil(S/32)] non-pad count per 32-token chunk
@@ -123,6 +125,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const h16* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, h16* __restrict__ out, int64_t rows, int H,
                  float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int nvec = H / 128;
     const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
@@ -148,6 +152,8 @@ template <bool kF16>
 __global__ void __launch_bounds__(1024)
 pool_normalize_kernel(const h16* __restrict__ hidden, const int32_t* __restrict__ mask,
                       float* __restrict__ out, int S, int H) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float smem_f[];
     float* s_part = smem_f;                     // [G][H]
     float* s_red = smem_f + kPoolGroups * H;    // [32] block-reduction scratch
@@ -256,9 +262,8 @@ int launch_embed_ln(const int32_t* ids, const float* word_emb, const float* pos_
     if (int rc = check_h(H)) return rc;
     const size_t smem = (S + (S + 31) / 32) * sizeof(int);
     auto kern = fp16 ? embed_ln_kernel<true> : embed_ln_kernel<false>;
-    kern<<<B, 256, smem, stream>>>(ids, word_emb, pos_emb, gamma, beta, out, S, H, vocab, max_pos,
-                                   pad_id, pos_mode, eps, err_flag_dev);
-    ARB_CHECK_CUDA(cudaGetLastError());
+    ARB_CHECK_CUDA(launch_kernel(kern, dim3(B), dim3(256), smem, stream, 1, ids, word_emb, pos_emb, gamma, beta, out, S, H,
+                                 vocab, max_pos, pad_id, pos_mode, eps, err_flag_dev));
     return ARB_OK;
 }
 
@@ -271,8 +276,7 @@ int launch_layernorm(const h16* x, const float* gamma, const float* beta, h16* o
     const int64_t cap = static_cast<int64_t>(num_sms()) * 32;
     const int grid = static_cast<int>(blocks_needed < cap ? blocks_needed : cap);
     auto kern = fp16 ? layernorm_kernel<true> : layernorm_kernel<false>;
-    kern<<<grid, 256, 0, stream>>>(x, gamma, beta, out, rows, H, eps);
-    ARB_CHECK_CUDA(cudaGetLastError());
+    ARB_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(256), 0, stream, 1, x, gamma, beta, out, rows, H, eps));
     return ARB_OK;
 }
 
@@ -285,8 +289,7 @@ int launch_pool_normalize(const h16* hidden, const int32_t* mask, float* out, in
     ARB_REQUIRE(threads <= 1024 && threads % 32 == 0, "pool_normalize: H=%d unsupported", H);
     const size_t smem = (kPoolGroups * H + 32 + kPoolGroups) * sizeof(float);
     auto kern = fp16 ? pool_normalize_kernel<true> : pool_normalize_kernel<false>;
-    kern<<<B, threads, smem, stream>>>(hidden, mask, out, S, H);
-    ARB_CHECK_CUDA(cudaGetLastError());
+    ARB_CHECK_CUDA(launch_kernel(kern, dim3(B), dim3(threads), smem, stream, 1, hidden, mask, out, S, H));
     return ARB_OK;
 }
 

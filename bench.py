@@ -18,7 +18,8 @@ Rank 0 prints ONE JSON line. `value` = chunks/s with token ids already resident 
 the same metric through the public API (`B200SentenceEncoder.encode`) from HOST numpy ids to HOST
 numpy embeddings, copies inside the timed region. `roofline` is the tensor-pipe roofline of the
 dominant kernel (the tcgen05 GEMM), timed live with CUDA events. Further records in the same line:
-`encode_s256` (the metric's own 256-token shape), `encode_bf16`, `search` (queries/s exact top-10
+`e2e_strings` (List[str] of ragged U[16,384]-token chunks through the native tokenizer, beside the
+same batches resident in HBM), `encode_s256` (the metric's own 256-token shape), `encode_bf16`, `search` (queries/s exact top-10
 over a 5M x 768 bf16 corpus, row-sharded over the ranks, with its roofline and a NumPy CPU
 baseline), `configs` (BASELINE configs[2], [3] and a 3-point configs[4] latency sweep), and
 `cpu_baseline` (the reference's encode loop on the host cores).
@@ -320,6 +321,63 @@ def run_b200(args):
     e2e = {"value": world * BATCH / (e2e_ms / 1e3), "unit": "chunks/s", "h2d_bytes_per_step": int(2 * BATCH * SEQ * 4),
            "d2h_bytes_per_step": int(BATCH * 768 * 4), "ms_per_step": e2e_ms,
            "api": "B200SentenceEncoder.encode((ids, mask) numpy, batch_size=1024) -> numpy float32 [1024,768]"}
+    # ------------------------------------------------------------------ e2e from List[str], ragged lengths
+    # The call the reference makes (generate_embeddings_parallel.py:146-153): strings in, float32 rows
+    # out. Chunks of U[16,384] tokens over a synthetic vocabulary (none ships offline), tokenised by the
+    # in-tree native tokenizer on a background thread, sorted by length, padded per batch. Beside it the
+    # same batches pre-tokenised and resident in HBM (what the GPU could do if the host cost nothing).
+    from arxiv_rag_b200.tokenizer import NativeWordPieceTokenizer
+    rs = np.random.RandomState(11 + rank)
+    letters = np.array(list("abcdefghijklmnopqrstuvwxyz"))
+    wset = {"".join(rs.choice(letters, rs.randint(2, 10))) for _ in range(30000)}
+    words = sorted(wset)
+    vocab = {t: i for i, t in enumerate(["<s>", "<pad>", "</s>", "[UNK]"] + words + list(".,;:()") +
+                                        ["##" + c for c in letters] + list(letters))}
+    enc.tokenizer = NativeWordPieceTokenizer(vocab, kind="mpnet", max_length=SEQ)
+    n_text = 8 * BATCH
+    wi = rs.randint(0, len(words), size=(n_text, SEQ))
+    n_tok = rs.randint(16, SEQ + 1, size=n_text)
+    texts = [" ".join(words[j] for j in wi[r, :n_tok[r] - 2]) for r in range(n_text)]
+    enc.encode(texts[:2 * BATCH], batch_size=BATCH)
+    barrier()
+    str_reps = 3
+    t0 = time.perf_counter()
+    for _ in range(str_reps):
+        enc.encode(texts, batch_size=BATCH, convert_to_numpy=True)
+    torch.cuda.synchronize()
+    str_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / str_reps
+    t_ids, t_mask = enc.tokenizer.tokenize_batch(texts)
+    t_len = t_mask.sum(1)
+    order = np.argsort(-np.array([len(t) for t in texts]), kind="stable")
+    dev_batches = []
+    for b0 in range(0, n_text, BATCH):
+        sel = order[b0:b0 + BATCH]
+        S = int(t_len[sel].max())
+        dev_batches.append((torch.from_numpy(np.ascontiguousarray(t_ids[sel, :S])).to(dev),
+                            torch.from_numpy(np.ascontiguousarray(t_mask[sel, :S])).to(dev)))
+    for d_i, d_m in dev_batches[:2]:
+        enc.encode_tokens(d_i, d_m, out)
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(str_reps):
+        for d_i, d_m in dev_batches:
+            enc.encode_tokens(d_i, d_m, out)
+    r1.record()
+    barrier()
+    res_ms = max_over_ranks(r0.elapsed_time(r1)) / str_reps
+    t0 = time.perf_counter()
+    enc.tokenizer.tokenize_batch(texts)
+    tok_s = time.perf_counter() - t0
+    e2e_strings = {"value": world * n_text / (str_ms / 1e3), "unit": "chunks/s", "ms_per_pass": str_ms,
+                   "device_resident": world * n_text / (res_ms / 1e3), "ratio": res_ms / str_ms,
+                   "chunks_per_pass_per_gpu": n_text, "tokens_mean": float(t_len.mean()),
+                   "tokenizer_chunks_per_s": n_text / tok_s, "tokenizer_threads": enc.tokenizer.num_threads,
+                   "h2d_bytes_per_pass": int(sum(2 * a.numel() * 4 for a, _ in dev_batches)),
+                   "d2h_bytes_per_pass": int(n_text * 768 * 4),
+                   "api": "B200SentenceEncoder.encode(List[str] of U[16,384]-token chunks, batch_size=1024) -> numpy float32; "
+                          "native WordPiece tokenizer (arb_tokenizer_encode), synthetic 30k vocabulary"}
+    del dev_batches, texts
     enc.close()
     del enc, ids
     torch.cuda.empty_cache()
@@ -576,7 +634,7 @@ def run_b200(args):
                        "parallelism": f"dp{world} (chunk batches sharded, no collective)",
                        "l2": "inputs rotate over 4 batches; per-step activations 6.6 GB >> 126 MB L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "encode_s256": encode_s256, "encode_bf16": encode_bf16, "search": search, "configs": configs,
+            "e2e_strings": e2e_strings, "encode_s256": encode_s256, "encode_bf16": encode_bf16, "search": search, "configs": configs,
             "unit_norm_check": checksum, "gflop_per_chunk": gfc,
         })
     if dist.is_initialized():
