@@ -258,11 +258,7 @@ static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B
     // Query-time batches: the forward is 63 short kernels; launch them programmatically dependent so
     // each one's set-up and weight prefetch overlap its predecessor (common.cuh: pdl_scope).
     // ARB_PDL=0 never, 2 always, default: up to kPdlMaxTokens tokens.
-    static const int pdl_mode = []() {
-        const char* e = getenv("ARB_PDL");
-        return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 1;
-    }();
-    pdl_scope pdl(pdl_mode == 2 || (pdl_mode == 1 && T <= kPdlMaxTokens));
+    pdl_scope pdl(T <= kPdlMaxTokens);
     int rc;
     if ((rc = launch_embed_ln(ids, m->word_emb, m->pos_emb, m->emb_g, m->emb_b, m->h, B, S, H,
                               c.vocab_size, c.max_position_embeddings, c.pad_token_id, c.position_mode,

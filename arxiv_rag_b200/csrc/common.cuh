@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/arxiv_rag_b200.h"  // ARB_OK / ARB_ERR_* codes
 
@@ -60,9 +61,19 @@ inline bool& pdl_flag() {
     static thread_local bool on = false;
     return on;
 }
+// ARB_PDL=0 never, 2 always, default 1: where the launcher says the call is latency-bound.
+inline int pdl_env_mode() {
+    static const int mode = []() {
+        const char* e = getenv("ARB_PDL");
+        return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 1;
+    }();
+    return mode;
+}
 struct pdl_scope {
     bool prev;
-    explicit pdl_scope(bool on) : prev(pdl_flag()) { pdl_flag() = on; }
+    explicit pdl_scope(bool latency_bound) : prev(pdl_flag()) {
+        pdl_flag() = pdl_env_mode() == 2 || (pdl_env_mode() == 1 && latency_bound);
+    }
     ~pdl_scope() { pdl_flag() = prev; }
 };
 

@@ -10,7 +10,7 @@ from arxiv_rag_b200.search import CorpusIndex
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 6_250_000
 S = int(os.environ.get("LAT_S", 64))
 dev = torch.device("cuda:0")
-enc = B200SentenceEncoder(None, max_batch=64, max_seq=S, dtype=os.environ.get("LAT_DTYPE", "fp16"), seed=0)
+enc = B200SentenceEncoder(None, max_batch=int(os.environ.get("LAT_MAXB", 64)), max_seq=S, dtype=os.environ.get("LAT_DTYPE", "fp16"), seed=0)
 ncu = os.environ.get("LAT_NCU") == "1"
 if os.environ.get("LAT_GEMM_MODE"):
     from arxiv_rag_b200 import _lib
@@ -41,7 +41,7 @@ if ncu:
     sys.exit(0)
 
 if os.environ.get("LAT_ENCODE_ONLY") == "1":
-    for Q in (1, 2, 8, 16, 32, 64):
+    for Q in [int(x) for x in os.environ.get("LAT_QS", "1,2,8,16,32,64").split(",")]:
         ids = torch.randint(4, 30000, (Q, S), device=dev, dtype=torch.int32)
         mask = torch.ones((Q, S), device=dev, dtype=torch.int32)
         print(f"Q={Q:3d} S={S}: encode plain {timeit(lambda: enc.encode_tokens(ids, mask)):7.1f} us  "
