@@ -39,6 +39,19 @@ struct GemmTileIter {
     }
 };
 
+// Narrow variant for query-time batches (a handful of row blocks): 128 x 128 tiles, so twice as many
+// SMs pull weights (a CTA streams at ~0.15 TB/s whatever the tile), 32 KB stages in a 6-deep ring,
+// and 1 KB after the staging tiles where the two epilogue groups (64 columns each) combine their row
+// statistics into the one partial per 128 columns the consumers expect.
+constexpr int kGemmNarrowBN = 128;
+constexpr int kGemmNarrowStages = 6;
+using GemmNarrowSmem = PipeSmem<kGemmNarrowBN, kGemmNarrowStages, 2 * kStageTileBytes + kBM * 8>;
+// ARB_GEMM_NARROW=0 keeps 128 x 256 tiles for every single-CTA launch (A/B)
+static const bool g_gemm_narrow = []() {
+    const char* e = getenv("ARB_GEMM_NARROW");
+    return !(e && e[0] == '0');
+}();
+
 // 0 = auto (pairs when there are more 256-row blocks than CTA pairs), 1 = single CTA, 2 = CTA pairs
 static int g_gemm_mode = 0;
 void set_gemm_mode(int mode) { g_gemm_mode = mode; }
@@ -163,12 +176,14 @@ __device__ __forceinline__ float gelu_f16_mode(float x) {
 
 // OutT = h16 (16-bit activations in the kF16 format) or float. k2Cta: launched as clusters of two
 // CTAs that share one 256 x 256 tile through tcgen05 cta_group::2 (see umma_pipe.cuh).
-template <int EPI, bool kF16, typename OutT, bool k2Cta, bool kColSmem = false>
+template <int EPI, bool kF16, typename OutT, bool k2Cta, bool kColSmem = false, int kBN = kGemmBN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
               const float* __restrict__ bias, int64_t M, int N, int K, const LnFoldArgs fold, const uint32_t idesc) {
-    constexpr int BN = kGemmBN;
+    constexpr int BN = kBN;
+    constexpr bool kNarrow = kBN != kGemmBN;
+    static_assert(!kNarrow || (kBN == kGemmNarrowBN && !k2Cta && !kColSmem), "narrow tiles: single-CTA schedule only");
     constexpr int CW = 128 / static_cast<int>(sizeof(OutT));  // columns per staging chunk
     constexpr int CPG = (BN / 2) / CW;                        // chunks per group per tile
     constexpr bool kLnIn = EPI == EPI_LNIN_BIAS || EPI == EPI_LNIN_BIAS_GELU;
@@ -177,7 +192,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     constexpr bool kLnRes = EPI == EPI_BIAS_LNRES_STATS;
     constexpr bool kStats = EPI == EPI_BIAS_LNRES_STATS || EPI == EPI_BIAS_RES_STATS;
     static_assert(!kColSmem || (k2Cta && EPI == EPI_BIAS_LNRES_STATS), "resident column vectors: pair kernel, LN(residual) epilogue");
-    using SM = typename std::conditional<kColSmem, Gemm2ColSmem, typename std::conditional<k2Cta, Gemm2Smem, GemmSmem>::type>::type;
+    using SM = typename std::conditional<kNarrow, GemmNarrowSmem,
+        typename std::conditional<kColSmem, Gemm2ColSmem, typename std::conditional<k2Cta, Gemm2Smem, GemmSmem>::type>::type>::type;
     using Iter = typename std::conditional<k2Cta, Gemm2TileIter, GemmTileIter>::type;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // SWIZZLE_128B tiles need a 1024-byte aligned base; align by hand (the launcher adds slack).
@@ -467,10 +483,22 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
                     }
                 }
             }
-            if constexpr (kStats) {
+            if constexpr (kStats && !kNarrow) {
                 // this thread covered columns [row_b + 128 grp, +128) of its row: one partial
                 if (any_live && grow < M)
                     fold.stats_out[static_cast<int64_t>((row_b >> 7) + grp) * M + grow] = make_float2(osum, osq);
+            }
+            if constexpr (kStats && kNarrow) {
+                // the groups covered 64 columns each: group 1 hands its sums over through shared memory
+                // and group 0 writes the partial of the 128 columns (second barrier: the slots are free again)
+                float2* comb = reinterpret_cast<float2*>(sm.pre() + 2 * kStageTileBytes);
+                if (grp == 1) comb[trow] = make_float2(osum, osq);
+                named_bar_sync(4, kEpiThreads);
+                if (grp == 0 && any_live && grow < M) {
+                    const float2 o = comb[trow];
+                    fold.stats_out[static_cast<int64_t>(row_b >> 7) * M + grow] = make_float2(osum + o.x, osq + o.y);
+                }
+                named_bar_sync(4, kEpiThreads);
             }
             if (++acc == 2) {
                 acc = 0;
@@ -528,6 +556,24 @@ static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb
         ARB_CHECK_CUDA(launch_kernel(kern, dim3(static_cast<unsigned>(nclusters * 2)), dim3(kGemmThreads), smem, stream, 2, ta, tb,
                                      tc, tr, bias, M, N, K, fold, umma_idesc_16bit(2 * kBM, kGemmBN, kF16)));
         return ARB_OK;
+    }
+    if constexpr (sizeof(OutT) == 2) {
+        // a handful of row blocks (query-time batches): narrow tiles put twice as many SMs on the weights
+        const int64_t wide_tiles = ((M + kBM - 1) / kBM) * ((N + kGemmBN - 1) / kGemmBN);
+        if (g_gemm_narrow && wide_tiles * 2 <= num_sms()) {
+            if (!make_tmap_bf16_k64(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), kGemmNarrowBN)) {
+                set_error("cuTensorMapEncodeTiled failed (B narrow tile)");
+                return ARB_ERR_CUDA;
+            }
+            auto nkern = gemm16_kernel<EPI, kF16, OutT, false, false, kGemmNarrowBN>;
+            constexpr int nsmem = GemmNarrowSmem::kExtraOffset + 1024;
+            static_assert(nsmem <= 232448, "narrow GEMM shared memory exceeds 227 KB");
+            ARB_CHECK_CUDA(set_max_smem_once(nkern, nsmem));
+            const int64_t ntiles = ((M + kBM - 1) / kBM) * ((N + kGemmNarrowBN - 1) / kGemmNarrowBN);
+            ARB_CHECK_CUDA(launch_kernel(nkern, dim3(static_cast<unsigned>(ntiles)), dim3(kGemmThreads), nsmem, stream, 1, ta, tb, tc, tr,
+                                         bias, M, N, K, fold, umma_idesc_16bit(kBM, kGemmNarrowBN, kF16)));
+            return ARB_OK;
+        }
     }
     auto kern = gemm16_kernel<EPI, kF16, OutT, false>;
     constexpr int smem = GemmSmem::kExtraOffset + 1024;  // +1024: alignment slack
