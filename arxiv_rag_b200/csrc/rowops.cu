@@ -89,8 +89,10 @@ embed_ln_kernel(const int32_t* __restrict__ ids, const float* __restrict__ word_
     }
     __syncthreads();
 
+    // gridDim.y CTAs share a sequence (each recomputed the positions above): a token costs a warp ~3 us
+    // of dependent gather latency, so a lone 64-token query wants 8 CTAs, not 8 tokens per warp in turn
     const int nvec = H / 128;
-    for (int s = warp; s < S; s += nwarps) {
+    for (int s = static_cast<int>(blockIdx.y) * nwarps + warp; s < S; s += nwarps * static_cast<int>(gridDim.y)) {
         int id = row_ids[s];
         if (id < 0 || id >= vocab) {
             // torch's embedding raises on such an id. Report it through the handle's status word
@@ -262,7 +264,10 @@ int launch_embed_ln(const int32_t* ids, const float* word_emb, const float* pos_
     if (int rc = check_h(H)) return rc;
     const size_t smem = (S + (S + 31) / 32) * sizeof(int);
     auto kern = fp16 ? embed_ln_kernel<true> : embed_ln_kernel<false>;
-    ARB_CHECK_CUDA(launch_kernel(kern, dim3(B), dim3(256), smem, stream, 1, ids, word_emb, pos_emb, gamma, beta, out, S, H,
+    int gy = (4 * num_sms()) / B;  // enough CTAs to cover the SMs a few times over, never more than one warp pass each
+    if (gy > (S + 7) / 8) gy = (S + 7) / 8;
+    if (gy < 1) gy = 1;
+    ARB_CHECK_CUDA(launch_kernel(kern, dim3(B, gy), dim3(256), smem, stream, 1, ids, word_emb, pos_emb, gamma, beta, out, S, H,
                                  vocab, max_pos, pad_id, pos_mode, eps, err_flag_dev));
     return ARB_OK;
 }
