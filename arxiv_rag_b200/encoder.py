@@ -117,7 +117,7 @@ class B200SentenceEncoder:
             if convert_to_tensor:
                 self.check_status(synchronize=True)
                 return out[0] if single else out
-            res = out.cpu().numpy()
+            res = self._to_host(out)
             self.check_status()
             return res[0] if single else res
         ids, mask = self._tokenize(sentences)
@@ -130,15 +130,26 @@ class B200SentenceEncoder:
             with torch.cuda.device(self.device):
                 for sel in self._batches(order, lengths, bs):
                     S = max(int(lengths[sel].max()), 1)  # pad to the longest row of the batch
-                    d_ids, d_mask = self._to_device(ids[sel, :S], mask[sel, :S])
-                    emb = self.encode_tokens(d_ids, d_mask)
-                    out[torch.from_numpy(sel).to(out.device)] = emb
+                    d_ids, d_mask, d_rows = self._to_device(ids[sel, :S], mask[sel, :S], sel)
+                    out.index_copy_(0, d_rows, self.encode_tokens(d_ids, d_mask))
         if convert_to_tensor:
             self.check_status(synchronize=True)
             return out[0] if single else out
-        res = out.cpu().numpy()  # synchronises the stream
+        res = self._to_host(out)  # synchronises the stream
         self.check_status()
         return res[0] if single else res
+
+    def _to_host(self, out) -> np.ndarray:
+        """Device rows -> numpy through page-locked memory (torch's caching host allocator recycles the
+        block once the returned array is dropped): a pageable `.cpu()` of 1 M x 768 floats runs at a
+        few GB/s and sits, un-overlapped, at the end of every `encode` call."""
+        torch = self._torch
+        if out.numel() * out.element_size() > (1 << 30):  # do not page-lock gigabytes for one result
+            return out.cpu().numpy()
+        host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+        host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(out.device).synchronize()
+        return host.numpy()
 
     @staticmethod
     def _is_text(sentences) -> bool:
@@ -184,9 +195,8 @@ class B200SentenceEncoder:
                 rows = np.argsort(-lengths, kind="stable")
                 for part in self._batches(rows, lengths, bs):  # a bf16 handle takes its short rows apart
                     S = max(int(lengths[part].max()), 1)
-                    d_ids, d_mask = self._to_device(ids[part, :S], mask[part, :S])
-                    emb = self.encode_tokens(d_ids, d_mask)
-                    out[torch.from_numpy(sel[part]).to(out.device)] = emb
+                    d_ids, d_mask, d_rows = self._to_device(ids[part, :S], mask[part, :S], sel[part])
+                    out.index_copy_(0, d_rows, self.encode_tokens(d_ids, d_mask))
         return out
 
     def _batches(self, order: np.ndarray, lengths: np.ndarray, bs: int):
@@ -282,26 +292,33 @@ class B200SentenceEncoder:
             ids, mask = ids[:, :self.max_seq], mask[:, :self.max_seq]  # tokenizer-style truncation
         return ids.astype(np.int32, copy=False), mask.astype(np.int32, copy=False)
 
-    def _to_device(self, ids: np.ndarray, mask: np.ndarray):
+    def _to_device(self, ids: np.ndarray, mask: np.ndarray, rows: np.ndarray | None = None):
         """Pinned staging + async H2D on the current stream. Two pinned buffers of the handle's
         capacity, used alternately and sliced per batch: filling one overlaps the copy out of the
-        other, and no shape ever needs a new pinned allocation."""
+        other, and no shape ever needs a new pinned allocation. `rows` (the batch's positions in the
+        caller's order) ride in the same copy: a separate pageable H2D would make the driver wait for
+        the stream to drain first, i.e. serialise the host with every batch's forward."""
         torch = self._torch
         B, S = ids.shape
         if self._staging is None:
-            cap = 2 * self.max_batch * self.max_seq
+            cap = 2 * self.max_batch * self.max_seq + self.max_batch
             self._staging = [[torch.empty(cap, dtype=torch.int32, pin_memory=True), torch.cuda.Event()]
                              for _ in range(2)]
             self._staging_next = 0
         st, ev = self._staging[self._staging_next]
         self._staging_next ^= 1
         ev.synchronize()  # the previous H2D out of this pinned buffer must have drained
-        view = st[:2 * B * S].view(2, B, S)
-        view[0].numpy()[...] = ids
-        view[1].numpy()[...] = mask
+        n = 2 * B * S
+        view = st[:n + (B if rows is not None else 0)]
+        host = view.numpy()
+        host[:B * S].reshape(B, S)[...] = ids
+        host[B * S:n].reshape(B, S)[...] = mask
+        if rows is not None:
+            host[n:] = rows
         dev = view.to(f"cuda:{self.device}", non_blocking=True)
         ev.record()
-        return dev[0], dev[1]
+        d_ids, d_mask = dev[:B * S].view(B, S), dev[B * S:n].view(B, S)
+        return (d_ids, d_mask) if rows is None else (d_ids, d_mask, dev[n:].long())
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -174,7 +174,7 @@ class WordPieceTokenizer:
 
 class NativeWordPieceTokenizer(WordPieceTokenizer):
     """Same constructor and results as `WordPieceTokenizer`; `tokenize_batch` runs in the library.
-    num_threads: worker threads per call (default: min(16, cores))."""
+    num_threads: worker threads per call (default: min(16, cores / LOCAL_WORLD_SIZE))."""
 
     def __init__(self, vocab, kind: str = "mpnet", do_lower_case: bool = True, max_length: int = 384,
                  num_threads: int | None = None):
@@ -185,7 +185,9 @@ class NativeWordPieceTokenizer(WordPieceTokenizer):
         from . import _lib
 
         self._libmod, self._C = _lib, C
-        self.num_threads = int(num_threads) if num_threads else min(16, os.cpu_count() or 1)
+        # default: up to 16 threads, but only this rank's share of the cores (one process per GPU under torchrun)
+        share = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+        self.num_threads = int(num_threads) if num_threads else min(16, share)
         toks = [t.encode("utf-8", "surrogatepass") for t in self.vocab]
         offs = np.zeros(len(toks) + 1, np.int64)
         np.cumsum([len(t) for t in toks], out=offs[1:])
