@@ -564,7 +564,7 @@ int arb_set_search_mode(int32_t mode) {
 }
 
 int arb_set_gemm_mode(int32_t mode) {
-    ARB_REQUIRE(mode >= 0 && mode <= 2, "gemm mode %d must be 0 (auto), 1 (single CTA) or 2 (CTA pairs)", mode);
+    ARB_REQUIRE(mode >= 0 && mode <= 3, "gemm mode %d must be 0 (auto), 1 (single CTA), 2 (CTA pairs) or 3 (single CTA, narrow tiles)", mode);
     set_gemm_mode(mode);
     return ARB_OK;
 }

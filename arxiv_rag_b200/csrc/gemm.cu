@@ -52,7 +52,7 @@ static const bool g_gemm_narrow = []() {
     return !(e && e[0] == '0');
 }();
 
-// 0 = auto (see launch_gemm_impl), 1 = single CTA, 2 = CTA pairs
+// 0 = auto (see launch_gemm_impl), 1 = single CTA 128x256, 2 = CTA pairs, 3 = single CTA 128x128
 static int g_gemm_mode = 0;
 constexpr int64_t kGemmPairMinRows = 32 * kBM;
 void set_gemm_mode(int mode) { g_gemm_mode = mode; }
@@ -181,7 +181,8 @@ template <int EPI, bool kF16, typename OutT, bool k2Cta, bool kColSmem = false, 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
-              const float* __restrict__ bias, int64_t M, int N, int K, const LnFoldArgs fold, const uint32_t idesc) {
+              const float* __restrict__ bias, int64_t M, int N, int K, const LnFoldArgs fold, const uint32_t idesc,
+              const uint32_t a_box_bytes) {
     constexpr int BN = kBN;
     constexpr bool kNarrow = kBN != kGemmBN;
     static_assert(!kNarrow || (kBN == kGemmNarrowBN && !k2Cta && !kColSmem), "narrow tiles: single-CTA schedule only");
@@ -236,7 +237,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     if (warp == 0) {
         if (elect_one()) {
             if constexpr (k2Cta) pipe2_produce(sm, &tmap_a, &tmap_b, it, kblocks, rank, kEvictNormal, kEvictLast);
-            else pipe_produce(sm, &tmap_a, &tmap_b, it, kblocks, kEvictNormal, kEvictLast);
+            else pipe_produce(sm, &tmap_a, &tmap_b, it, kblocks, kEvictNormal, kEvictLast,
+                              a_box_bytes ? a_box_bytes + static_cast<uint32_t>(SM::kBBytes) : 0u);
         }
     } else if (warp == 1) {
         if (elect_one()) {
@@ -557,24 +559,38 @@ static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb
         int64_t nclusters = num_sms() / 2;
         if (nclusters > tiles) nclusters = tiles;
         ARB_CHECK_CUDA(launch_kernel(kern, dim3(static_cast<unsigned>(nclusters * 2)), dim3(kGemmThreads), smem, stream, 2, ta, tb,
-                                     tc, tr, bias, M, N, K, fold, umma_idesc_16bit(2 * kBM, kGemmBN, kF16)));
+                                     tc, tr, bias, M, N, K, fold, umma_idesc_16bit(2 * kBM, kGemmBN, kF16), 0u));
         return ARB_OK;
     }
     if constexpr (sizeof(OutT) == 2) {
         // a handful of row blocks (query-time batches): narrow tiles put twice as many SMs on the weights
         const int64_t wide_tiles = ((M + kBM - 1) / kBM) * ((N + kGemmBN - 1) / kGemmBN);
-        if (g_gemm_narrow && wide_tiles * 2 <= num_sms()) {
+        if (g_gemm_mode == 3 || (g_gemm_mode == 0 && g_gemm_narrow && wide_tiles * 2 <= num_sms())) {
             if (!make_tmap_bf16_k64(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), kGemmNarrowBN)) {
                 set_error("cuTensorMapEncodeTiled failed (B narrow tile)");
                 return ARB_ERR_CUDA;
+            }
+            // fewer than 128 rows in all: load only those (rounded up to a swizzle atom). Half of every
+            // stage would otherwise be zero fill, through TMA's slow out-of-bounds path at that.
+            uint32_t a_box_bytes = 0;
+            if (M < kBM) {
+                const uint32_t a_rows = static_cast<uint32_t>((M + 7) / 8 * 8);
+                if (a_rows < static_cast<uint32_t>(kBM)) {
+                    if (!make_tmap_bf16_k64(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), a_rows)) {
+                        set_error("cuTensorMapEncodeTiled failed (A short tile)");
+                        return ARB_ERR_CUDA;
+                    }
+                    a_box_bytes = a_rows * 128u;
+                }
             }
             auto nkern = gemm16_kernel<EPI, kF16, OutT, false, false, kGemmNarrowBN>;
             constexpr int nsmem = GemmNarrowSmem::kExtraOffset + 1024;
             static_assert(nsmem <= 232448, "narrow GEMM shared memory exceeds 227 KB");
             ARB_CHECK_CUDA(set_max_smem_once(nkern, nsmem));
             const int64_t ntiles = ((M + kBM - 1) / kBM) * ((N + kGemmNarrowBN - 1) / kGemmNarrowBN);
-            ARB_CHECK_CUDA(launch_kernel(nkern, dim3(static_cast<unsigned>(ntiles)), dim3(kGemmThreads), nsmem, stream, 1, ta, tb, tc, tr,
-                                         bias, M, N, K, fold, umma_idesc_16bit(kBM, kGemmNarrowBN, kF16)));
+            const int64_t ngrid = ntiles < num_sms() ? ntiles : num_sms();
+            ARB_CHECK_CUDA(launch_kernel(nkern, dim3(static_cast<unsigned>(ngrid)), dim3(kGemmThreads), nsmem, stream, 1, ta, tb, tc, tr,
+                                         bias, M, N, K, fold, umma_idesc_16bit(kBM, kGemmNarrowBN, kF16), a_box_bytes));
             return ARB_OK;
         }
     }
@@ -585,7 +601,7 @@ static int launch_gemm_impl(const h16* A, int64_t lda, const h16* B, int64_t ldb
     const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + kGemmBN - 1) / kGemmBN);
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     ARB_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), smem, stream, 1, ta, tb, tc, tr, bias, M, N, K, fold,
-                                 umma_idesc_16bit(kBM, kGemmBN, kF16)));
+                                 umma_idesc_16bit(kBM, kGemmBN, kF16), 0u));
     return ARB_OK;
 }
 

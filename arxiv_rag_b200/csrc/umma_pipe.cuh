@@ -94,16 +94,19 @@ __device__ __forceinline__ void pipe_teardown(const SM& sm, int warp, uint32_t t
 // Producer: for every tile the iterator yields, stream its K-blocks through the ring.
 // TileIter: bool next(int& row_a, int& row_b) — first rows of the A and B tiles.
 template <class SM, class TileIter>
+// stage_tx: bytes one stage's two loads deliver, when the A box is shorter than the 128-row tile
+// (0 = full tiles). The MMA still reads 128 rows; the rows the box leaves untouched are never stored.
 __device__ __forceinline__ void pipe_produce(const SM& sm, const void* tmap_a, const void* tmap_b,
                                              TileIter it, int kblocks, uint64_t hint_a,
-                                             uint64_t hint_b) {
+                                             uint64_t hint_b, uint32_t stage_tx = 0) {
     int stage = 0;
     uint32_t phase = 0;
     int row_a, row_b;
+    const uint32_t tx = stage_tx ? stage_tx : static_cast<uint32_t>(SM::kStageBytes);
     while (it.next(row_a, row_b)) {
         for (int kb = 0; kb < kblocks; ++kb) {
             mbar_wait(sm.empty(stage), phase ^ 1);
-            mbar_arrive_expect_tx(sm.full(stage), SM::kStageBytes);
+            mbar_arrive_expect_tx(sm.full(stage), tx);
             tma_load_2d(tmap_a, sm.full(stage), sm.a(stage), kb * kBK, row_a, hint_a);
             tma_load_2d(tmap_b, sm.full(stage), sm.b(stage), kb * kBK, row_b, hint_b);
             if (++stage == SM::kStages) {

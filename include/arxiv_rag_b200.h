@@ -236,7 +236,8 @@ int arb_gemm16_lnfold(const void* A, int64_t lda, const void* B, int64_t ldb, vo
                       int32_t N, int32_t K, int32_t epilogue, int32_t dtype, void* stream);
 /* Tile schedule of the arb_gemm16* kernels (process-wide; for tests and benchmarks): 0 = auto,
  * 1 = one CTA per 128x256 tile (tcgen05 cta_group::1), 2 = CTA pairs sharing a 256x256 tile
- * (cta_group::2, thread-block clusters of two). Auto: pairs from 4096 rows up; below that single
+ * (cta_group::2, thread-block clusters of two), 3 = one CTA per 128x128 tile (16-bit outputs; other
+ * outputs fall back to 1). Auto: pairs from 4096 rows up; below that single
  * CTAs, with 128x128 tiles when the 128x256 tiles would fill less than half of the SMs (query-time
  * batches; ARB_GEMM_NARROW=0 disables). Kernel chains of small calls are launched programmatically
  * dependent (ARB_PDL=0 disables). */

@@ -110,9 +110,9 @@ def _row_partials(x16, parts):
     return torch.stack([blocks.sum(2), (blocks * blocks).sum(2)], dim=2).permute(1, 0, 2).contiguous()  # [parts, M, 2]
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("dt", ["bf16", "fp16"])
-@pytest.mark.parametrize("shape", [(777, 768, 768), (3000, 384, 384)])
+@pytest.mark.parametrize("shape", [(777, 768, 768), (3000, 384, 384), (70, 768, 3072)])
 def test_gemm_layernorm_fold(lib, cuda, dt, shape, mode):
     """The LayerNorm-folding epilogues the encoder uses instead of LayerNorm passes
     (modeling_mpnet.py:210 / :242 post-LN): a producer writes pre-LN rows + row partials
@@ -164,22 +164,23 @@ def test_gemm_layernorm_fold(lib, cuda, dt, shape, mode):
 
 
 def test_gemm_schedules_agree_bitwise(lib, cuda):
-    """Both schedules accumulate each output element over K in the same order, so they must agree
-    bit for bit — the encoder's result does not depend on which one `auto` picks."""
+    """All three schedules (128x256 single CTA, 256x256 CTA pairs, 128x128 narrow tiles) accumulate
+    each output element over K in the same order, so they must agree bit for bit — the encoder's
+    result does not depend on which one `auto` picks for a batch size."""
     torch.manual_seed(2)
     M, N, K = 3000, 768, 768
     A = (torch.randn(M, K, device=cuda) * 0.3).to(torch.bfloat16)
     B = (torch.randn(N, K, device=cuda) * 0.05).to(torch.bfloat16)
     bias = torch.randn(N, device=cuda)
     out = []
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         _lib.check(lib.arb_set_gemm_mode(mode))
         C = torch.zeros(M, N, device=cuda, dtype=torch.bfloat16)
         _lib.check(lib.arb_gemm16(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, bias.data_ptr(), 0, N, M, N, K, 1,
                                   _lib.ARB_DTYPE_BF16, _stream()))
         out.append(C)
     _lib.check(lib.arb_set_gemm_mode(0))
-    assert torch.equal(out[0], out[1])
+    assert torch.equal(out[0], out[1]) and torch.equal(out[0], out[2])
 
 
 def test_gemm_strided_operands(lib, cuda):

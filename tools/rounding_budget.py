@@ -29,11 +29,16 @@ F = {
 
 
 @torch.no_grad()
-def forward(arch, sd, ids, mask, w="f32", a="f32", p="f32", resid="same", gelu="erf"):
+def forward(arch, sd, ids, mask, w="f32", a="f32", p="f32", resid="same", gelu="erf", w_ffn=None, f_fmt=None, y_fmt=None,
+            w_up=None):
     """w / a / p: formats of the weights, the stored activations and the stored probabilities;
     resid: format of the stored pre-LN rows ('same' = activations' format)."""
     rw, ra, rp = F[w], F[a], F[p]
     rr = ra if resid == "same" else F[resid]
+    rw_dn = F[w_ffn] if w_ffn else rw   # FFN-down weights
+    rw_up = F[w_up] if w_up else rw     # FFN-up weights
+    rf = F[f_fmt] if f_fmt else ra      # stored GELU output (A operand of FFN-down)
+    ry = F[y_fmt] if y_fmt else rr      # stored pre-LN y rows (A operand of FFN-up and residual of FFN-down)
     t = lambda k: torch.as_tensor(np.asarray(sd[k])).float()
     ids = torch.as_tensor(np.asarray(ids)).long()
     mask = torch.as_tensor(np.asarray(mask)).long()
@@ -64,7 +69,7 @@ def forward(arch, sd, ids, mask, w="f32", a="f32", p="f32", resid="same", gelu="
         W = lambda n: t(pfx + n + ".weight")
         bia = lambda n: t(pfx + n + ".bias")
 
-        def lin_in(name, stored, exact, g, b):
+        def lin_in(name, stored, exact, g, b, rw=rw):
             if g is None:
                 return stored @ rw(W(name)).T + bia(name)
             mu = exact.mean(-1, keepdim=True)
@@ -83,12 +88,12 @@ def forward(arch, sd, ids, mask, w="f32", a="f32", p="f32", resid="same", gelu="
         c = ra(c).transpose(1, 2).reshape(B, S, H)
         res = xs if g_prev is None else ln_fold(xs, xe, g_prev, b_prev)
         ye = c @ rw(W("attention.attn.o")).T + bia("attention.attn.o") + res
-        ys = rr(ye)
+        ys = ry(ye)
         g1, b1 = t(pfx + "attention.LayerNorm.weight"), t(pfx + "attention.LayerNorm.bias")
-        pre = lin_in("intermediate.dense", ys, ye, g1, b1)
+        pre = lin_in("intermediate.dense", ys, ye, g1, b1, rw_up)
         f = torch.nn.functional.gelu(pre) if gelu == "erf" else 0.5 * pre * (1 + torch.tanh(0.8 * pre + 0.03475 * pre ** 3))
-        f = ra(f)
-        xe = f @ rw(W("output.dense")).T + bia("output.dense") + ln_fold(ys, ye, g1, b1)
+        f = rf(f)
+        xe = f @ rw_dn(W("output.dense")).T + bia("output.dense") + ln_fold(ys, ye, g1, b1)
         xs = rr(xe)
         g_prev, b_prev = t(pfx + "output.LayerNorm.weight"), t(pfx + "output.LayerNorm.bias")
     h = ra(ln_fold(xs, xe, g_prev, b_prev))
@@ -142,6 +147,9 @@ def main():
         ("w fp16, a bf16, resid fp32", dict(w="fp16", a="bf16", p="fp16", resid="f32")),
         ("w fp16, a fp16, resid bf16", dict(w="fp16", a="fp16", p="fp16", resid="bf16")),
         ("all fp16", dict(w="fp16", a="fp16", p="fp16")),
+        ("fp16, FFN-down bf16 (W2, gelu out)", dict(w="fp16", a="fp16", p="fp16", w_ffn="bf16", f_fmt="bf16")),
+        ("fp16, FFN up+down bf16 (y bf16)", dict(w="fp16", a="fp16", p="fp16", w_ffn="bf16", w_up="bf16", f_fmt="bf16", y_fmt="bf16")),
+        ("fp16, FFN up+down W bf16 only", dict(w="fp16", a="fp16", p="fp16", w_ffn="bf16", w_up="bf16")),
     ]:
         out = forward(arch, sd, ids, mask, **kw)
         cos = (out * ref2).sum(1)
