@@ -86,6 +86,7 @@ SIGNATURES = {
     "arb_topk_merge": (C.c_int, [_VP, _VP, _I32, _I64, _I32, _VP, _VP, _VP]),
     "arb_topk_search_launches": (C.c_int, [_I32]),
     "arb_set_gemm_mode": (C.c_int, [_I32]),
+    "arb_set_pdl_mode": (C.c_int, [_I32]),
     "arb_set_search_mode": (C.c_int, [_I32]),
     "arb_gemm16_lnfold": (C.c_int, [_VP, _I64, _VP, _I64, _VP, _I64, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _I32, _I32, _VP,
                                     C.c_float, _I64, _I32, _I32, _I32, _I32, _VP]),

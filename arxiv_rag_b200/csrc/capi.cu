@@ -246,6 +246,14 @@ constexpr int kShortSeq = 32;
 
 constexpr int64_t kPdlMaxTokens = 16384;
 
+int& pdl_mode_ref() {
+    static int mode = []() {
+        const char* e = getenv("ARB_PDL");
+        return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 1;
+    }();
+    return mode;
+}
+
 static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B, int S, float* out,
                         cudaStream_t st) {
     const ArbMpnetConfig& c = m->cfg;
@@ -560,6 +568,12 @@ int arb_topk_exchange_status(const void* own_buf_dev) { return topk_exchange_sta
 int arb_set_search_mode(int32_t mode) {
     ARB_REQUIRE(mode >= 0 && mode <= 2, "search mode %d must be 0 (auto), 1 (single CTA) or 2 (CTA pairs)", mode);
     set_search_mode(mode);
+    return ARB_OK;
+}
+
+int arb_set_pdl_mode(int32_t mode) {
+    ARB_REQUIRE(mode >= 0 && mode <= 2, "pdl mode %d must be 0 (never), 1 (latency-bound calls) or 2 (always)", mode);
+    pdl_mode_ref() = mode;
     return ARB_OK;
 }
 

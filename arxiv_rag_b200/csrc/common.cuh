@@ -62,13 +62,8 @@ inline bool& pdl_flag() {
     return on;
 }
 // ARB_PDL=0 never, 2 always, default 1: where the launcher says the call is latency-bound.
-inline int pdl_env_mode() {
-    static const int mode = []() {
-        const char* e = getenv("ARB_PDL");
-        return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 1;
-    }();
-    return mode;
-}
+int& pdl_mode_ref();  // capi.cu: process-wide, initialised from ARB_PDL, set by arb_set_pdl_mode
+inline int pdl_env_mode() { return pdl_mode_ref(); }
 struct pdl_scope {
     bool prev;
     explicit pdl_scope(bool latency_bound) : prev(pdl_flag()) {

@@ -242,6 +242,10 @@ int arb_gemm16_lnfold(const void* A, int64_t lda, const void* B, int64_t ldb, vo
  * batches; ARB_GEMM_NARROW=0 disables). Kernel chains of small calls are launched programmatically
  * dependent (ARB_PDL=0 disables). */
 int arb_set_gemm_mode(int32_t mode);
+/* Programmatic dependent launch of kernel chains (process-wide; initial value from ARB_PDL): 0 = never,
+ * 1 = calls the library considers latency-bound (an encode of <= 16384 tokens), 2 = every chain.
+ * Results are bit-identical in every mode; the GPU tests compare them. */
+int arb_set_pdl_mode(int32_t mode);
 /* C[M,N] = epi(A[M,K] . B[N,K]^T + bias[N]) (+ R[M,N]); 16-bit operands, fp32 accumulate. */
 int arb_gemm16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                const float* bias, const void* R, int64_t ldr, int64_t M, int32_t N, int32_t K,

@@ -234,6 +234,43 @@ def test_cuda_graph_path_is_identical(cuda, full_model):
     enc.close()
 
 
+@pytest.mark.parametrize("shape", [(1, 16), (3, 64), (40, 96)])
+def test_launch_and_tile_schedules_are_bit_identical(cuda, full_model, shape):
+    """A forward is a chain of 63 kernels. For query-time batches the chain is launched
+    programmatically dependent (a kernel's set-up overlaps its predecessor; arb_set_pdl_mode) and
+    the GEMMs run narrow 128x128 tiles (arb_set_gemm_mode 0 picks them, 1 never does). Neither may
+    change a bit of the result — a missed dependency in the overlapped launches would."""
+    import torch
+
+    from arxiv_rag_b200 import _lib
+
+    arch, sd, _ = full_model
+    B, S = shape
+    enc = _encoder(arch, sd, "fp16", max_batch=64, max_seq=128)
+    lib = _lib.lib()
+    ids, mask = eo.synthetic_tokens(B, S, seed=77)
+    d_ids, d_mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    outs = {}
+    try:
+        for pdl in (0, 2):
+            for gemm in (0, 1):
+                _lib.check(lib.arb_set_pdl_mode(pdl))
+                _lib.check(lib.arb_set_gemm_mode(gemm))
+                for rep in range(3):  # repeated: overlapped launches race, if they race, only sometimes
+                    outs[(pdl, gemm, rep)] = enc.encode_tokens(d_ids, d_mask).clone()
+        _lib.check(lib.arb_set_pdl_mode(2))
+        _lib.check(lib.arb_set_gemm_mode(0))
+        outs["graph"] = enc.encode_tokens_graphed(d_ids, d_mask).clone()
+    finally:
+        _lib.check(lib.arb_set_pdl_mode(1))
+        _lib.check(lib.arb_set_gemm_mode(0))
+    torch.cuda.synchronize()
+    first = outs[(0, 1, 0)]
+    for key, o in outs.items():
+        assert torch.equal(o, first), key
+    enc.close()
+
+
 def test_reference_worker_api(cuda, full_model):
     """generate_embeddings_worker / generate_embeddings_parallel (reference :131-269): tuple shape,
     row type, order; compared with the oracle's restatement of the same control flow."""
