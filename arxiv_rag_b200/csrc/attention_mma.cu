@@ -301,8 +301,8 @@ int launch_attention_mma(const h16* qkv, const float* rel_bias, int max_rel, con
 }
 
 // impl: 0 = auto, 1 = mma.sync, 2 = tcgen05, 3 = tcgen05 with sub-block pipelining (experiment, only in
-// builds with -DARB_WITH_ATTENTION_TC2). auto = impl 2 when the shape allows (head dim 64,
-// 64 <= S <= 384), else mma.sync; ARB_ATTN_IMPL overrides auto for A/B runs.
+// builds with -DARB_WITH_ATTENTION_TC2). impl 2 covers head dim 64, 1 <= S <= 384; auto picks it for
+// 64 <= S <= 384, else mma.sync; ARB_ATTN_IMPL overrides auto for A/B runs.
 int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
                      h16* ctx, int B, int S, int heads, int dh, bool fp16, int impl, cudaStream_t stream) {
     ARB_REQUIRE(impl >= 0 && impl <= 3, "attention: impl %d must be 0 (auto), 1 (mma.sync), 2 or 3 (tcgen05)", impl);
@@ -313,7 +313,9 @@ int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const i
         }();
         impl = forced >= 1 && forced <= 3 ? forced : 2;
         if (impl == 3 && !(rel_bias != nullptr && attention_tc2_supported(S, dh) && S >= kAttnTcMinSeq)) impl = 1;
-        if (impl == 2 && !(rel_bias != nullptr && attention_tc_supported(S, dh))) impl = 1;
+        // the tcgen05 kernel also runs S < 64 (parity-tested), but there a forward takes the same time with
+        // either kernel (443 vs 440 us at Q=1, S=16): auto keeps mma.sync below one 64-key block
+        if (impl == 2 && !(rel_bias != nullptr && attention_tc_supported(S, dh) && S >= kAttnTcMinSeq)) impl = 1;
     }
     if (impl == 3) return launch_attention_tc2(qkv, rel_bias, max_rel, mask, ctx, B, S, heads, dh, fp16, stream);
     if (impl == 2) return launch_attention_tc(qkv, rel_bias, max_rel, mask, ctx, B, S, heads, dh, fp16, stream);

@@ -470,7 +470,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
 }
 
-bool attention_tc_supported(int S, int dh) { return dh == 64 && S >= 64 && S <= 2 * kAtMaxKh; }
+bool attention_tc_supported(int S, int dh) { return dh == 64 && S >= 1 && S <= 2 * kAtMaxKh; }
 
 int launch_attention_tc(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
                         h16* ctx, int B, int S, int heads, int dh, bool fp16, cudaStream_t stream) {

@@ -358,8 +358,6 @@ def test_attention(lib, cuda, dt, case, impl):
     tdt, code, _ = DT[dt]
     tol = 1.5e-2 if dt == "bf16" else 2e-3
     B, S, lens = case
-    if impl == 2 and S < 64:
-        pytest.skip("tcgen05 attention kernel covers 64 <= S <= 384; shorter sequences use the mma.sync kernel")
     nH, dh, P = 12, 64, 512
     H = nH * dh
     torch.manual_seed(6)
