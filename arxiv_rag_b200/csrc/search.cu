@@ -35,6 +35,8 @@ struct SearchPlan {
     int grid;      // CTAs
 };
 
+constexpr int kSharedSplitMaxChunks = 1000;  // ~390 MB of bf16 rows: see make_plan
+
 // 0 = auto (pairs as soon as there is more than one query tile), 1 = single CTA, 2 = pairs
 static int g_search_mode = 0;
 void set_search_mode(int mode) { g_search_mode = mode; }
@@ -55,18 +57,35 @@ static SearchPlan make_plan(int64_t Q, int64_t N, int k) {
     int best = 1;
     double best_eff = -1.0;
     const int max_split = p.nchunks < 4 ? 1 : (p.nchunks / 4 < 4 * G ? p.nchunks / 4 : 4 * G);
-    for (int s = 1; s <= max_split; ++s) {
-        const int cps = (p.nchunks + s - 1) / s;
-        const int s_eff = (p.nchunks + cps - 1) / cps;  // splits actually non-empty
-        if (s_eff != s) continue;
-        const int64_t items = static_cast<int64_t>(p.nq) * s;
-        const int64_t rounds = (items + G - 1) / G;
-        const double eff = (static_cast<double>(p.nq) * p.nchunks / G) / (static_cast<double>(rounds) * (cps + warm));
-        if (eff > best_eff + 0.02) {
-            best_eff = eff;
-            best = s;
+    // Several query tiles stream the same split side by side and share its chunks through L2 only
+    // while they stay within the cache of each other. Over a long split they drift apart (measured:
+    // 2 171-chunk splits at Q = 4096 over 5 M rows re-read the corpus 2.7 times from DRAM), so splits
+    // walked by 12 or more tile pairs are kept short: 2.5-6 % faster at Q = 4096 / 8192 over 5 M rows,
+    // DRAM reads 2.7x -> 1.8x the corpus. With few tiles per split (Q = 700: +5 %, 2048: +2.5 %) and from
+    // half of the pairs per split up (Q = 16 384: +2 %, 32 768: +8 %) it is the other way round, so no
+    // limit there. ARB_SEARCH_MAX_CPS overrides the length (0 = no limit).
+    static const int env_max_cps = []() {
+        const char* e = getenv("ARB_SEARCH_MAX_CPS");
+        return e ? atoi(e) : -1;
+    }();
+    const int max_cps = env_max_cps >= 0 ? env_max_cps : kSharedSplitMaxChunks;
+    // (only where a fresh item warms up in a few chunks: the shared-memory lists of k > 16 need long splits)
+    const int min_split = (p.nq >= 12 && 2 * p.nq <= G && max_cps > 0 && k <= 16) ? (p.nchunks + max_cps - 1) / max_cps : 1;
+    for (int first = min_split < max_split ? min_split : max_split; best_eff < 0.0; first = 1) {
+        for (int s = first; s <= max_split; ++s) {
+            const int cps = (p.nchunks + s - 1) / s;
+            const int s_eff = (p.nchunks + cps - 1) / cps;  // splits actually non-empty
+            if (s_eff != s) continue;
+            const int64_t items = static_cast<int64_t>(p.nq) * s;
+            const int64_t rounds = (items + G - 1) / G;
+            const double eff = (static_cast<double>(p.nq) * p.nchunks / G) / (static_cast<double>(rounds) * (cps + warm));
+            if (eff > best_eff + 0.02) {
+                best_eff = eff;
+                best = s;
+            }
+            if (items >= 16ll * G && s >= first + 8) break;
         }
-        if (items >= 16ll * G) break;
+        if (first == 1) break;
     }
     p.nsplit = best;
     p.cps = (p.nchunks + best - 1) / best;
