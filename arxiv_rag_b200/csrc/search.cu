@@ -94,23 +94,85 @@ static SearchPlan make_plan(int64_t Q, int64_t N, int k) {
     return p;
 }
 
+__device__ __forceinline__ void st_relaxed_gpu(int* p, int v) {
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // Yields the (query-tile row, corpus chunk row) sequence of this CTA's items.
 // nq = query tiles (single CTA) or query-tile PAIRS (CTA-pair schedule, where this CTA takes tile
 // 2 * pair + rank: qmul = 2, qadd = rank).
+//
+// Pacing (`progress` != nullptr: the TMA-issuing thread of a work unit only). The query tiles that
+// walk one split at the same time share its chunks through L2 only while they stay close together;
+// left alone they drift apart and each chunk comes from DRAM two or three times. So a unit publishes
+// the chunk it is about to load every kPaceEvery chunks and looks at ONE peer per check, round-robin
+// over the units that walk the same split in the same round (units are dealt items round-robin, so
+// round = item / step, and every item of a round is started by some unit: a wait always ends; it is
+// bounded all the same): it does not run more than kPaceWindow chunks ahead of a peer it has seen. The
+// peer's slot is requested one check before it is judged, so the TMA-issuing thread never stalls on
+// the load (a blocking scan of all peers cost 10-40 % of the kernel). progress[] lives in the caller's workspace and needs no
+// initialisation: an item's slot is reset when the item starts, a finished item's slot holds its
+// full length, and whatever else a peer's slot holds either ends the wait at once or makes the
+// leader wait for a peer that is about to start.
+constexpr int kPaceEvery = 4;
+constexpr int kPaceWindow = 16;
+constexpr int kPaceMaxSpins = 4000;  // x ~50 ns: give up after ~0.2 ms, never hang
+
 struct SearchTileIter {
     int item, step, items, nq, cps, nchunks, qmul, qadd;
     int chunk = 0, chunk_end = 0, row_q = 0;
+    int* progress = nullptr;
+    int cur = -1, chunk_begin = 0, peer_lo = 0, peer_hi = 0, rot = 0, seen_peer = 0, seen = 1 << 30;
     __device__ __forceinline__ SearchTileIter(int first, int step_, int items_, int nq_, int cps_,
                                               int nchunks_, int qmul_ = 1, int qadd_ = 0)
         : item(first), step(step_), items(items_), nq(nq_), cps(cps_), nchunks(nchunks_), qmul(qmul_), qadd(qadd_) {}
     __device__ __forceinline__ bool next(int& row_a, int& row_b) {
         while (chunk >= chunk_end) {
-            if (item >= items) return false;
+            if (progress != nullptr && cur >= 0) st_relaxed_gpu(progress + cur, cps + kPaceWindow);  // done: never holds anyone back
+            if (item >= items) {
+                cur = -1;
+                return false;
+            }
             const int split = item / nq;
             row_q = ((item % nq) * qmul + qadd) * kBM;
             chunk = split * cps;
             chunk_end = min(chunk + cps, nchunks);
+            if (progress != nullptr) {
+                cur = item;
+                chunk_begin = chunk;
+                const int round = item / step;
+                peer_lo = max(split * nq, round * step);
+                peer_hi = min(min((split + 1) * nq, (round + 1) * step), items);
+                seen = 1 << 30;
+                rot = cur - peer_lo;
+                st_relaxed_gpu(progress + cur, 0);
+            }
             item += step;
+        }
+        if (progress != nullptr) {
+            const int c = chunk - chunk_begin;
+            if ((c & (kPaceEvery - 1)) == 0) {
+                st_relaxed_gpu(progress + cur, c);
+                // judge the peer whose slot was read at the previous check (the load has long landed: no
+                // stall on the TMA-issuing thread), re-polling only if it really lags
+                for (int spin = 0; seen + kPaceWindow + kPaceEvery < c && spin < kPaceMaxSpins; ++spin) {
+                    __nanosleep(50);
+                    seen = ld_relaxed_gpu(progress + seen_peer);
+                }
+                // and request the next peer's slot, round-robin over the units on this split
+                const int n = peer_hi - peer_lo;
+                if (n > 1) {
+                    rot = rot + 1 < n ? rot + 1 : 0;
+                    if (peer_lo + rot == cur) rot = rot + 1 < n ? rot + 1 : 0;
+                    seen_peer = peer_lo + rot;
+                    seen = ld_relaxed_gpu(progress + seen_peer);
+                }
+            }
         }
         row_a = row_q;
         row_b = chunk * kSBN;
@@ -205,7 +267,7 @@ __global__ void __launch_bounds__(kSearchThreads, 1)
 search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                    const __grid_constant__ CUtensorMap tmap_c, float* __restrict__ part_scores,
                    int32_t* __restrict__ part_ids, int64_t Q, int64_t N, int D, int k, int nq, int cps,
-                   int nchunks, int nsplit, int cbuf) {
+                   int nchunks, int nsplit, int cbuf, int* __restrict__ progress) {
     using SM = PipeSmem<kSBN, kSStages, 0, kPair ? 2 : 1>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     SM sm{smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)};
@@ -225,8 +287,10 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     if (warp == 0) {
         // queries are re-read by every chunk -> keep in L2; the corpus streams through once per split
         if (elect_one()) {
-            if constexpr (kPair) pipe2_produce(sm, &tmap_q, &tmap_c, it, kblocks, rank, kEvictLast, kEvictNormal);
-            else pipe_produce(sm, &tmap_q, &tmap_c, it, kblocks, kEvictLast, kEvictNormal);
+            SearchTileIter pit = it;
+            if (rank == 0 && nq > 1) pit.progress = progress;  // pacing among the tiles that share a split
+            if constexpr (kPair) pipe2_produce(sm, &tmap_q, &tmap_c, pit, kblocks, rank, kEvictLast, kEvictNormal);
+            else pipe_produce(sm, &tmap_q, &tmap_c, pit, kblocks, kEvictLast, kEvictNormal);
         }
     } else if (warp == 1) {
         if (elect_one()) {
@@ -906,7 +970,8 @@ size_t search_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
     const SearchPlan p = make_plan(Q, N, k);
     const size_t per = static_cast<size_t>(p.nsplit) * Q * k;
     const size_t pad = static_cast<size_t>(padded_queries(Q, p.pair)) * D * 2;
-    return align_up(per * 4, 256) + align_up(per * 4, 256) + align_up(pad, 256);
+    const size_t prog = static_cast<size_t>(p.nq) * p.nsplit * sizeof(int);
+    return align_up(per * 4, 256) + align_up(per * 4, 256) + align_up(pad, 256) + align_up(prog, 256);
 }
 
 // q / corpus: rows of D 16-bit words (bf16 values, or — tf32 — the two halves of D/2 fp32 values).
@@ -930,6 +995,14 @@ static int launch_search_16(const uint16_t* q, const uint16_t* corpus, int64_t Q
     float* part_scores = reinterpret_cast<float*>(workspace);
     int32_t* part_ids = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) + align_up(per * 4, 256));
 
+    // pacing slots, one per work item (SearchTileIter); ARB_SEARCH_PACE=0 switches the pacing off (A/B)
+    static const bool pace = []() {
+        const char* e = getenv("ARB_SEARCH_PACE");
+        return !(e && e[0] == '0');
+    }();
+    int* progress = pace ? reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + 2 * align_up(per * 4, 256) +
+                                                  align_up(static_cast<size_t>(padded_queries(Q, p.pair)) * D * 2, 256))
+                         : nullptr;
     const int64_t Qp = padded_queries(Q, p.pair);
     if (Qp > 0) {  // whole query tiles only: see padded_queries
         uint16_t* qpad = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(workspace) + 2 * align_up(per * 4, 256));
@@ -972,7 +1045,7 @@ static int launch_search_16(const uint16_t* q, const uint16_t* corpus, int64_t Q
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         ARB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tc, part_scores, part_ids, Q, N, D, k, p.nq, p.cps, p.nchunks,
-                                          p.nsplit, cbuf));
+                                          p.nsplit, cbuf, progress));
         return ARB_OK;
     };
     int lrc;
