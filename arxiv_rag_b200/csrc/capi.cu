@@ -263,7 +263,7 @@ static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B
     const bool a16 = m->fp16 || use_f16_copy;
     const bool fmt = a16;  // one 16-bit format for every operand of this call
     const std::vector<LayerDev>& layers = use_f16_copy ? m->layers_f16 : m->layers;
-    // Query-time batches: the forward is 63 short kernels; launch them programmatically dependent so
+    // Query-time batches: the forward is 62 short kernels; launch them programmatically dependent so
     // each one's set-up and weight prefetch overlap its predecessor (common.cuh: pdl_scope).
     // ARB_PDL=0 never, 2 always, default: up to kPdlMaxTokens tokens.
     pdl_scope pdl(T <= kPdlMaxTokens);
@@ -312,8 +312,9 @@ static int mpnet_encode(Mpnet* m, const int32_t* ids, const int32_t* mask, int B
             if ((rc = launch_gemm16_fold(m->ffn, I, d.w_out, I, m->tmp, H, d.b_out, m->h1, H, T, H, I, EPI_BIAS_LNRES_STATS, fd, fmt, st))) return rc;
         }
         const LayerDev& last = layers[c.num_layers - 1];
-        if ((rc = launch_layernorm(m->tmp, last.ln2_g, last.ln2_b, m->h, T, H, c.layer_norm_eps, a16, st))) return rc;
-        return launch_pool_normalize(m->h, mask, out, B, S, H, a16, st);
+        // the last LayerNorm rides in the pooling kernel (pre-LN rows + their row partials)
+        return launch_pool_ln_normalize(m->tmp, m->stats_x, H / 128, last.ln2_g, last.ln2_b, c.layer_norm_eps, mask, out, B, S, H,
+                                        a16, st);
     }
     for (int l = 0; l < c.num_layers; ++l) {
         const LayerDev& d = layers[l];
@@ -420,7 +421,7 @@ int64_t arb_mpnet_device_bytes(void* handle) { return handle ? static_cast<Mpnet
 int arb_mpnet_launches_per_encode(void* handle) {
     if (!handle) return 0;
     const Mpnet* m = static_cast<Mpnet*>(handle);
-    if (m->fold_ln) return 3 + 5 * m->cfg.num_layers;  // embed, 5 per layer, final LayerNorm, pool
+    if (m->fold_ln) return 2 + 5 * m->cfg.num_layers;  // embed, 5 per layer, pool (with the last LayerNorm)
     return 2 + 7 * m->cfg.num_layers;
 }
 

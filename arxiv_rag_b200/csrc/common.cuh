@@ -31,7 +31,7 @@ const char* get_error();
     } while (0)
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel, device and size instead of on
-// every launch (the attribute is sticky; the encoder launches 63 kernels per forward).
+// every launch (the attribute is sticky; the encoder launches 62 kernels per forward).
 template <class Kern>
 inline cudaError_t set_max_smem_once(Kern kern, int bytes) {
     struct Slot { const void* fn; int dev; int bytes; };
@@ -56,7 +56,7 @@ inline cudaError_t set_max_smem_once(Kern kern, int bytes) {
 // and blocks in `griddepcontrol.wait` (ptx.cuh: pdl_wait) before it touches anything the predecessor
 // wrote. Every kernel launched this way executes pdl_wait on all threads, so completion stays
 // transitive along the chain. Used for small token counts (query-time latency), where the forward is
-// 63 short kernels and launch + set-up are a third of each.
+// 62 short kernels and launch + set-up are a third of each.
 inline bool& pdl_flag() {
     static thread_local bool on = false;
     return on;

@@ -60,6 +60,11 @@ int launch_embed_ln(const int32_t* ids, const float* word_emb, const float* pos_
 int launch_layernorm(const h16* x, const float* gamma, const float* beta, h16* out, int64_t rows,
                      int H, float eps, bool fp16, cudaStream_t stream);
 // masked mean over tokens then L2 normalise: hidden [B,S,H], mask int32 [B,S] -> fp32 [B,H]
+// pooling + L2 normalisation with the last LayerNorm applied on the fly from the pre-LN rows and their
+// row partials ([parts][B*S] (sum, sum of squares)): the folded forward's final step
+int launch_pool_ln_normalize(const h16* pre, const float2* stats, int parts, const float* gamma, const float* beta,
+                             float eps, const int32_t* mask, float* out, int B, int S, int H, bool fp16,
+                             cudaStream_t stream);
 int launch_pool_normalize(const h16* hidden, const int32_t* mask, float* out, int B, int S, int H,
                           bool fp16, cudaStream_t stream);
 // out[i] = cos(emb[i], emb[i-1]) (out[0] = 1): the adjacent-sentence similarity of semantic chunking

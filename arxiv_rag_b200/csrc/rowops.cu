@@ -212,6 +212,97 @@ pool_normalize_kernel(const h16* __restrict__ hidden, const int32_t* __restrict_
     }
 }
 
+// The last LayerNorm folded into the pooling: reads the PRE-LayerNorm rows and the per-row partials
+// their producer wrote (gemm.cu EPI_BIAS_LNRES_STATS), so no LayerNorm pass is left anywhere in the
+// folded forward. mean_t(LN(x_t)) = gamma * mean_t((x_t - mu_t) rstd_t) + beta, over unmasked tokens.
+template <bool kF16>
+__global__ void __launch_bounds__(1024)
+pool_ln_normalize_kernel(const h16* __restrict__ pre, const float2* __restrict__ stats, int parts, int64_t total_rows,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                         const int32_t* __restrict__ mask, float* __restrict__ out, int S, int H) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ float smem_f[];
+    float* s_part = smem_f;                     // [G][H]
+    float* s_red = smem_f + kPoolGroups * H;    // [32] block-reduction scratch
+    float* s_cnt = s_red + 32;                  // [G] per-group token counts
+    float* s_rs = s_cnt + kPoolGroups;          // [S] rstd of each token's row
+    float* s_nm = s_rs + S;                     // [S] -mean * rstd
+    const int b = blockIdx.x;
+    const int tpg = H / 4;  // threads per group
+    const int g = threadIdx.x / tpg, c = threadIdx.x % tpg;
+    const h16* hb = pre + static_cast<int64_t>(b) * S * H;
+    const int32_t* mb = mask + static_cast<int64_t>(b) * S;
+    const float inv_h = 1.0f / static_cast<float>(H);
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        if (mb[s] == 0) continue;
+        const int64_t row = static_cast<int64_t>(b) * S + s;
+        float su = 0.f, sq = 0.f;
+        for (int p = 0; p < parts; ++p) {
+            const float2 t = __ldg(stats + static_cast<int64_t>(p) * total_rows + row);
+            su += t.x;
+            sq += t.y;
+        }
+        const float mean = su * inv_h;
+        const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, sq * inv_h), 0.f) + eps);
+        s_rs[s] = rstd;
+        s_nm[s] = -mean * rstd;
+    }
+    __syncthreads();
+
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float cnt_g = 0.f;
+    for (int s = g; s < S; s += kPoolGroups) {
+        const float m = static_cast<float>(mb[s]);
+        cnt_g += m;
+        if (m != 0.f) {
+            const uint2 u = __ldg(reinterpret_cast<const uint2*>(hb + static_cast<int64_t>(s) * H + c * 4));
+            const float2 a = unpack16x2<kF16>(u.x), d = unpack16x2<kF16>(u.y);
+            const float rs = s_rs[s], nm = s_nm[s];
+            acc.x += m * fmaf(a.x, rs, nm);
+            acc.y += m * fmaf(a.y, rs, nm);
+            acc.z += m * fmaf(d.x, rs, nm);
+            acc.w += m * fmaf(d.y, rs, nm);
+        }
+    }
+    *reinterpret_cast<float4*>(s_part + g * H + c * 4) = acc;
+    if (c == 0) s_cnt[g] = cnt_g;
+    __syncthreads();
+    float cnt = 0.f;
+#pragma unroll
+    for (int j = 0; j < kPoolGroups; ++j) cnt += s_cnt[j];
+
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sq = 0.f;
+    if (g == 0) {
+#pragma unroll
+        for (int j = 0; j < kPoolGroups; ++j) {
+            const float4 p = *reinterpret_cast<const float4*>(s_part + j * H + c * 4);
+            v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+        }
+        const float inv = 1.0f / fmaxf(cnt, 1e-9f);  // Pooling: sum / clamp(sum_mask, min=1e-9)
+        const float wb = cnt * inv;                  // 1 for any real row, 0 for an all-pad row (-> zero vector)
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c * 4));
+        const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c * 4));
+        v.x = fmaf(gm.x, v.x * inv, bt.x * wb);
+        v.y = fmaf(gm.y, v.y * inv, bt.y * wb);
+        v.z = fmaf(gm.z, v.z * inv, bt.z * wb);
+        v.w = fmaf(gm.w, v.w * inv, bt.w * wb);
+        sq = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    float tot = 0.f;
+    const int nw = blockDim.x >> 5;
+    for (int j = 0; j < nw; ++j) tot += s_red[j];
+    if (g == 0) {
+        const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);  // F.normalize(p=2, eps=1e-12)
+        *reinterpret_cast<float4*>(out + static_cast<int64_t>(b) * H + c * 4) =
+            make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+    }
+}
+
 // cos(e[i], e[i-1]) for consecutive rows — TextChunker._cosine_similarity
 // (text_processor.py:1601-1605) over the adjacent sentence pairs of _chunk_semantic (:1547-1561).
 // One warp per row; out[0] = 1.
@@ -295,6 +386,21 @@ int launch_pool_normalize(const h16* hidden, const int32_t* mask, float* out, in
     const size_t smem = (kPoolGroups * H + 32 + kPoolGroups) * sizeof(float);
     auto kern = fp16 ? pool_normalize_kernel<true> : pool_normalize_kernel<false>;
     ARB_CHECK_CUDA(launch_kernel(kern, dim3(B), dim3(threads), smem, stream, 1, hidden, mask, out, S, H));
+    return ARB_OK;
+}
+
+int launch_pool_ln_normalize(const h16* pre, const float2* stats, int parts, const float* gamma, const float* beta,
+                             float eps, const int32_t* mask, float* out, int B, int S, int H, bool fp16,
+                             cudaStream_t stream) {
+    ARB_REQUIRE(pre && stats && gamma && beta && mask && out, "pool_ln_normalize: null pointer");
+    ARB_REQUIRE(B > 0 && S > 0 && parts > 0, "pool_ln_normalize: bad shape B=%d S=%d parts=%d", B, S, parts);
+    if (int rc = check_h(H)) return rc;
+    const int threads = (H / 4) * kPoolGroups;
+    ARB_REQUIRE(threads <= 1024 && threads % 32 == 0, "pool_ln_normalize: H=%d unsupported", H);
+    const size_t smem = (kPoolGroups * H + 32 + kPoolGroups + 2 * static_cast<size_t>(S)) * sizeof(float);
+    auto kern = fp16 ? pool_ln_normalize_kernel<true> : pool_ln_normalize_kernel<false>;
+    ARB_CHECK_CUDA(launch_kernel(kern, dim3(B), dim3(threads), smem, stream, 1, pre, stats, parts,
+                                 static_cast<int64_t>(B) * S, gamma, beta, eps, mask, out, S, H));
     return ARB_OK;
 }
 
