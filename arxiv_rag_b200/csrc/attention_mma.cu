@@ -23,6 +23,7 @@ namespace arb {
 
 // shortest sequence the encoder sends to the tcgen05 attention in auto mode
 constexpr int kAttnTcMinSeq = 64;
+constexpr int kAttnSplitMinSeq = 256;  // auto: attention_tc3 above this length
 
 constexpr int kAttnThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -301,22 +302,27 @@ int launch_attention_mma(const h16* qkv, const float* rel_bias, int max_rel, con
 }
 
 // impl: 0 = auto, 1 = mma.sync, 2 = tcgen05, 3 = tcgen05 with sub-block pipelining (experiment, only in
-// builds with -DARB_WITH_ATTENTION_TC2). impl 2 covers head dim 64, 1 <= S <= 384; auto picks it for
-// 64 <= S <= 384, else mma.sync; ARB_ATTN_IMPL overrides auto for A/B runs.
+// builds with -DARB_WITH_ATTENTION_TC2), 4 = tcgen05 with 16 softmax warps (attention_tc3.cu). impl 2 and 4
+// cover head dim 64, 1 <= S <= 384; auto picks 2 for 64 <= S <= 256, 4 for 256 < S <= 384, else mma.sync;
+// ARB_ATTN_IMPL overrides auto for A/B runs.
 int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
                      h16* ctx, int B, int S, int heads, int dh, bool fp16, int impl, cudaStream_t stream) {
-    ARB_REQUIRE(impl >= 0 && impl <= 3, "attention: impl %d must be 0 (auto), 1 (mma.sync), 2 or 3 (tcgen05)", impl);
+    ARB_REQUIRE(impl >= 0 && impl <= 4, "attention: impl %d must be 0 (auto), 1 (mma.sync), 2, 3 or 4 (tcgen05)", impl);
     if (impl == 0) {
         static const int forced = []() {
             const char* e = getenv("ARB_ATTN_IMPL");
             return e ? atoi(e) : 0;
         }();
-        impl = forced >= 1 && forced <= 3 ? forced : 2;
+        // 16 softmax warps (attention_tc3.cu) from three query tiles / 160-key halves up: 5-9 % faster than
+        // the 8-warp kernel at S = 272..384, equal at 256, slower below (fewer columns per thread than latency)
+        impl = forced >= 1 && forced <= 4 ? forced : (S > kAttnSplitMinSeq ? 4 : 2);
+        if (impl == 4 && !(rel_bias != nullptr && attention_tc3_supported(S, dh) && S >= kAttnTcMinSeq)) impl = 1;
         if (impl == 3 && !(rel_bias != nullptr && attention_tc2_supported(S, dh) && S >= kAttnTcMinSeq)) impl = 1;
         // the tcgen05 kernel also runs S < 64 (parity-tested), but there a forward takes the same time with
         // either kernel (443 vs 440 us at Q=1, S=16): auto keeps mma.sync below one 64-key block
         if (impl == 2 && !(rel_bias != nullptr && attention_tc_supported(S, dh) && S >= kAttnTcMinSeq)) impl = 1;
     }
+    if (impl == 4) return launch_attention_tc3(qkv, rel_bias, max_rel, mask, ctx, B, S, heads, dh, fp16, stream);
     if (impl == 3) return launch_attention_tc2(qkv, rel_bias, max_rel, mask, ctx, B, S, heads, dh, fp16, stream);
     if (impl == 2) return launch_attention_tc(qkv, rel_bias, max_rel, mask, ctx, B, S, heads, dh, fp16, stream);
     return launch_attention_mma(qkv, rel_bias, max_rel, mask, ctx, B, S, heads, dh, fp16, stream);

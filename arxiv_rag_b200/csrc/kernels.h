@@ -82,6 +82,10 @@ bool attention_tc2_supported(int S, int dh);
 int launch_attention_tc2(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
                          h16* ctx, int B, int S, int heads, int dh, bool fp16, cudaStream_t stream);
 bool attention_tc_supported(int S, int dh);
+// attention_tc3.cu: the same schedule with 16 softmax warps (two column threads per query row and key half)
+bool attention_tc3_supported(int S, int dh);
+int launch_attention_tc3(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
+                         h16* ctx, int B, int S, int heads, int dh, bool fp16, cudaStream_t stream);
 int launch_attention_tc(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
                         h16* ctx, int B, int S, int heads, int dh, bool fp16, cudaStream_t stream);
 

@@ -315,7 +315,7 @@ def _attention_reference(qkv, relb, mask, B, S, nH, dh, P):
     return (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * S, H)
 
 
-@pytest.mark.parametrize("impl", [2, 3])
+@pytest.mark.parametrize("impl", [2, 3, 4])
 @pytest.mark.parametrize("dt", ["bf16", "fp16"])
 def test_attention_wide_bias_and_moving_maximum(lib, cuda, dt, impl):
     """What a trained relative-position table and peaked attention do to the softmax: biases spread
@@ -346,7 +346,38 @@ def test_attention_wide_bias_and_moving_maximum(lib, cuda, dt, impl):
     assert _rel_err(ctx[live], ref[live]) < tol
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3])
+@pytest.mark.parametrize("impl", [1, 2, 4])
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+@pytest.mark.parametrize("case", [(2, 384, [384, 250]), (3, 320, [320, 319, 40]), (2, 200, [200, 7])])
+def test_attention_bucketed_bias(lib, cuda, dt, case, impl):
+    """The relative-position table as MPNet really builds it: 32 buckets, constant beyond |j - i| = 91
+    (modeling_mpnet.py:343-360). The 16-warp kernel reads one table entry per 32-key chunk where the
+    chunk lies wholly in a constant tail; the result must not change."""
+    tdt, code, _ = DT[dt]
+    tol = 1.5e-2 if dt == "bf16" else 2e-3
+    B, S, lens = case
+    nH, dh, P = 12, 64, 512
+    H = nH * dh
+    torch.manual_seed(9)
+    qkv = torch.randn(B * S, 3 * H, device=cuda).to(tdt)
+    emb = torch.randn(32, nH, device=cuda) * 0.7
+    rel = torch.arange(-(P - 1), P)
+    buckets = torch.tensor([lib.arb_mpnet_relative_bucket(int(r), 32, 128) for r in rel], device=cuda)
+    relb = emb[buckets].t().contiguous()  # [nH, 2P-1], entry (j - i) + P - 1
+    mask = (torch.arange(S, device=cuda)[None, :] < torch.tensor(lens, device=cuda)[:, None]).int().contiguous()
+    ctx = torch.zeros(B * S, H, device=cuda, dtype=tdt)
+    _lib.check(lib.arb_attention16(qkv.data_ptr(), relb.data_ptr(), P, mask.data_ptr(), ctx.data_ptr(), B, S, nH, dh, code, impl, _stream()))
+    q, k, v = [t.float().view(B, S, nH, dh).transpose(1, 2) for t in qkv.split(H, dim=1)]
+    idx = torch.arange(S, device=cuda)
+    bias = relb[:, idx[None, :] - idx[:, None] + (P - 1)]
+    ext = (1.0 - mask[:, None, None, :].float()) * torch.finfo(torch.float32).min
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh) + bias[None] + ext, -1) @ v).transpose(1, 2).reshape(B * S, H)
+    live = (torch.arange(S, device=cuda)[None, :] < torch.tensor(lens, device=cuda)[:, None]).reshape(B * S)
+    assert torch.isfinite(ctx.float()).all()
+    assert _rel_err(ctx[live], ref[live]) < tol
+
+
+@pytest.mark.parametrize("impl", [1, 2, 3, 4])
 @pytest.mark.parametrize("dt", ["bf16", "fp16"])
 @pytest.mark.parametrize("case", [(3, 64, [64, 1, 17]), (4, 100, [100, 37, 0, 99]), (2, 384, [384, 200]), (1, 5, [3]),
                                   (5, 256, [256, 255, 130, 3, 0]), (3, 200, [200, 101, 100]), (2, 33, [33, 20]),

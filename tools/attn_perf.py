@@ -3,11 +3,17 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from arxiv_rag_b200 import _lib
 lib = _lib.lib()
-for (B, S) in [(1024, 384), (1024, 256), (1024, 128), (4096, 64)]:
+shapes = [tuple(int(x) for x in t.split("x")) for t in os.environ["ATTN_SHAPES"].split(",")] if os.environ.get("ATTN_SHAPES") \
+    else [(1024, 384), (1024, 256), (1024, 128), (4096, 64)]
+for (B, S) in shapes:
     H = 768
     for dt, code in ((torch.float16, _lib.ARB_DTYPE_F16), (torch.bfloat16, _lib.ARB_DTYPE_BF16)):
         qkv = torch.randn(B * S, 3 * H, device="cuda").to(dt)
-        relb = torch.randn(12, 1023, device="cuda")
+        if os.environ.get("ATTN_RANDOM_BIAS") == "1":
+            relb = torch.randn(12, 1023, device="cuda")
+        else:  # the table as MPNet builds it: 32 buckets, constant beyond |j - i| = 91
+            bk = torch.tensor([lib.arb_mpnet_relative_bucket(int(r), 32, 128) for r in range(-511, 512)], device="cuda")
+            relb = (torch.randn(32, 12, device="cuda") * 0.7)[bk].t().contiguous()
         mask = torch.ones(B, S, device="cuda", dtype=torch.int32)
         ctx = torch.empty(B * S, H, device="cuda", dtype=dt)
         fl = 4.0 * B * 12 * S * S * 64
