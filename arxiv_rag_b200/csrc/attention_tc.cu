@@ -93,9 +93,9 @@ __host__ __device__ inline AtLayout at_layout(int Kh, int nqt) {
     L.nbias = nqt * kAtQT + 2 * Kh;                 // even
     L.bias_off = L.q_off + kAtQT * 128;
     L.mask_off = L.bias_off + 2 * (L.nbias + 2) * 4;  // two copies (shift 0 / shift 1), padded
-    L.exch_off = L.mask_off + 2 * (2 * Kh) * 4;       // one mask table per softmax group
+    L.exch_off = L.mask_off;                          // (no per-key mask table: chunk flags + key bitmasks after `red`)
     L.red_off = L.exch_off + 2 * 2 * kAtQT * 8;       // [parity][half][row] (c, l)
-    L.bar_off = (L.red_off + 32 * 4 + 7) & ~7;
+    L.bar_off = (L.red_off + 32 * 4 + 16 + 64 + 7) & ~7;  // + mask flags [half][8] (bytes) and key bitmasks [half][8]
     L.total = L.bar_off + 16 * 8 + 16;
     return L;
 }
@@ -166,6 +166,37 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, int nchunk, float scal
     }
     c_out = c;
     l_out = l;
+}
+
+// Masked keys (padding inside a batch, keys beyond S). Per 32-key chunk of a half: flag 0 = every key
+// valid, 1 = some, 2 = none, plus the chunk's key bitmask (one ballot while the item is set up).
+// A sequence with masked keys runs the SAME softmax code as a fully valid one: a pre-pass rewrites
+// the scores of the (few) partly masked chunks to -inf in TMEM, the main passes stop after the last
+// chunk that has a valid key, and a post-pass zeroes P of the chunks behind it. A length-sorted batch
+// of real chunks masks a few trailing keys of almost every row; the former per-key mask reads on whole
+// rows cost 25-30 % of the kernel, and keeping a masked variant of the passes inline cost the
+// unmasked path 1-8 % through the kernel-wide register allocation.
+__device__ __forceinline__ void mask_prepass(uint32_t tS, int n_eff, const uint32_t* __restrict__ cbits,
+                                             const uint8_t* __restrict__ cflag) {
+    for (int cc = 0; cc < n_eff; ++cc) {
+        if (cflag[cc] == 0) continue;
+        const uint32_t w = cbits[cc];
+        uint32_t v[32];
+        tmem_ld_32x32(tS + cc * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (w >> j) & 1u ? v[j] : 0xff800000u;
+        tmem_st_32x16(tS + cc * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        tmem_st_32x16(tS + cc * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        tmem_st_wait();  // the main pass reads these columns again
+    }
+}
+template <bool kF16>
+__device__ __forceinline__ void mask_postpass(uint32_t tS, int n_eff, int nchunk) {
+    uint32_t z[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = 0u;
+    for (int cc = n_eff; cc < nchunk; ++cc) tmem_st_32x16(tS + cc * 16, z);
 }
 
 // kDefer: which softmax group combines the two key halves and stores the tile.
@@ -365,25 +396,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int quarter = warp & 3;               // TMEM lane quarter this warp may access
         const int r = quarter * 32 + lane;          // query row inside the tile
         const int bar_id = 1 + hh;
-        float* msk = reinterpret_cast<float*>(sm + L.mask_off) + hh * (2 * Kh);     // private mask table (0 / -inf)
+        uint8_t* cflag = reinterpret_cast<uint8_t*>(sm + L.red_off + 32 * 4) + hh * 8;           // this half's chunk flags
+        uint32_t* cbits = reinterpret_cast<uint32_t*>(sm + L.red_off + 32 * 4 + 16) + hh * 8;   // and key bitmasks
         float2* exch = reinterpret_cast<float2*>(sm + L.exch_off);                  // [parity][half][row] (c, l)
         const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
         const uint32_t tS = tmem + lane_sel + kAtColS + hh * kAtMaxKh;
         const int nchunk = Kh / 32;
-        const float* pm = msk + hh * Kh;
         int g = 0;
         for (int b = b_first; b < B; b += ngroups) {
-            // ---- per-item mask table (private to the group: no cross-group synchronisation)
+            // ---- per-item chunk flags and key bitmasks of this half (private to the group: no cross-group synchronisation)
             bar_sync_n(bar_id, 128);  // everyone is done with the previous item's table
             bool mine_clear = true, mine_on = false;
-            for (int j = r; j < 2 * Kh; j += 128) {
+            for (int j = r; j < 2 * Kh; j += 128) {  // a warp covers one 32-key chunk per step
                 const bool on = j < S && mask[static_cast<int64_t>(b) * S + j] != 0;
-                msk[j] = on ? 0.f : -INFINITY;
+                const uint32_t bal = __ballot_sync(0xffffffff, on);
+                if (lane == 0 && j >= hh * Kh && j < (hh + 1) * Kh) {
+                    cflag[(j - hh * Kh) >> 5] = bal == 0xffffffffu ? 0 : (bal != 0u ? 1 : 2);
+                    cbits[(j - hh * Kh) >> 5] = bal;
+                }
                 mine_clear &= on;
                 mine_on |= on;
             }
             const bool clear = bar_red_and(bar_id, 128, mine_clear);  // no masked / out-of-range key at all
-            const bool any_on = bar_red_or(bar_id, 128, mine_on);
+            const bool any_on = bar_red_or(bar_id, 128, mine_on);    // (the barriers also publish the flags)
+            int n_eff = nchunk;  // chunks up to the last one of this half with a valid key
+            if (!clear)
+                while (n_eff > 0 && cflag[n_eff - 1] == 2) --n_eff;
             for (int t = 0; t < nqt; ++t, ++g) {
                 const uint32_t ph = g & 1;
                 const int i = t * kAtQT + r;
@@ -409,9 +447,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                         tmem_st_32x16(tS + cc * 16, pk);
                     }
                 } else if (clear) {
-                    softmax_tile<kF16, false>(tS, nchunk, scale_log2e, bmax, pb2, pm, c, l);
+                    softmax_tile<kF16, false>(tS, nchunk, scale_log2e, bmax, pb2, nullptr, c, l);
                 } else {
-                    softmax_tile<kF16, true>(tS, nchunk, scale_log2e, bmax, pb2, pm, c, l);
+                    mask_prepass(tS, n_eff, cbits, cflag);
+                    c = 0.f;
+                    l = 0.f;
+                    if (n_eff > 0) softmax_tile<kF16, false>(tS, n_eff, scale_log2e, bmax, pb2, nullptr, c, l);
+                    mask_postpass<kF16>(tS, n_eff, nchunk);
                 }
                 tmem_st_wait();
                 tc_fence_before();

@@ -83,10 +83,10 @@ __host__ __device__ inline A3Layout a3_layout(int Kh, int nqt) {
     L.nbias = nqt * kA3QT + 2 * Kh;
     L.bias_off = L.q_off + kA3QT * 128;
     L.mask_off = L.bias_off + 2 * (L.nbias + 2) * 4;   // two copies (shift 0 / shift 1)
-    L.exch_off = L.mask_off + (2 * Kh) * 4;             // each half's group keeps only its own keys
+    L.exch_off = L.mask_off;                            // (no per-key mask table: chunk flags + key bitmasks after `red`)
     L.xmax_off = L.exch_off + 2 * 2 * 2 * kA3QT * 8;    // [parity][half][cs][row] (c, partial l)
     L.red_off = L.xmax_off + 2 * 2 * kA3QT * 4;         // [half][cs][row] raw maximum
-    L.bar_off = (L.red_off + 64 * 4 + 7) & ~7;
+    L.bar_off = (L.red_off + 64 * 4 + 16 + 64 + 7) & ~7;  // + mask flags [half][8] (bytes) and key bitmasks [half][8]
     L.total = L.bar_off + 16 * 8 + 16;
     return L;
 }
@@ -163,6 +163,31 @@ __device__ __forceinline__ float a3_emit(uint32_t tS, int nloc, float scale, flo
         tmem_st_32x16(tS + cc * 16, pk);  // inside the columns this thread has already read
     }
     return l;
+}
+
+// Masked keys: see attention_tc.cu (mask_prepass / mask_postpass) — partly masked chunks are rewritten to
+// -inf in TMEM first, the unmasked passes then run over the chunks up to the last one with a valid key,
+// and P of the chunks behind it is zeroed afterwards.
+__device__ __forceinline__ void a3_mask_prepass(uint32_t tS, int n_eff, const uint32_t* __restrict__ cbits,
+                                                const uint8_t* __restrict__ cflag) {
+    for (int cc = 0; cc < n_eff; ++cc) {
+        if (cflag[cc] == 0) continue;
+        const uint32_t w = cbits[cc];
+        uint32_t v[32];
+        tmem_ld_32x32(tS + cc * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (w >> j) & 1u ? v[j] : 0xff800000u;
+        tmem_st_32x16(tS + cc * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        tmem_st_32x16(tS + cc * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        tmem_st_wait();  // the main pass reads these columns again
+    }
+}
+__device__ __forceinline__ void a3_mask_postpass(uint32_t tS, int n_eff, int nloc) {
+    uint32_t z[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = 0u;
+    for (int cc = n_eff; cc < nloc; ++cc) tmem_st_32x16(tS + cc * 16, z);
 }
 
 template <bool kF16>
@@ -360,24 +385,33 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const int bar_id = 1 + hh;
         const int cb = cs == 0 ? 0 : n0;            // first chunk of this thread
         const int nloc = cs == 0 ? n0 : nchunk - n0;
-        float* msk = reinterpret_cast<float*>(sm + L.mask_off) + hh * Kh;  // this half's keys (0 / -inf)
+        uint8_t* cfl_half = reinterpret_cast<uint8_t*>(sm + L.red_off + 64 * 4) + hh * 8;           // this half's chunk flags
+        uint32_t* cbits_half = reinterpret_cast<uint32_t*>(sm + L.red_off + 64 * 4 + 16) + hh * 8; // and key bitmasks
+        const uint8_t* cflag = cfl_half + cb;
+        const uint32_t* cbits = cbits_half + cb;
         float2* exch = reinterpret_cast<float2*>(sm + L.exch_off);         // [parity][half][cs][row]
         float* xmax = reinterpret_cast<float*>(sm + L.xmax_off);           // [half][cs][row]
         const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
         const uint32_t tS = tmem + lane_sel + kA3ColS + hh * kA3MaxKh + cb * 32;
-        const float* pm = msk + cb * 32;
         int g = 0;
         for (int b = b_first; b < B; b += ngroups) {
             a3_bar_sync(bar_id, 256);  // everyone is done with the previous item's table
             bool mine_clear = true, mine_on = false;
-            for (int j = cs * 128 + r; j < 2 * Kh; j += 256) {
+            for (int j = cs * 128 + r; j < 2 * Kh; j += 256) {  // a warp covers one 32-key chunk per step
                 const bool on = j < S && mask[static_cast<int64_t>(b) * S + j] != 0;
-                if (j >= hh * Kh && j < (hh + 1) * Kh) msk[j - hh * Kh] = on ? 0.f : -INFINITY;
+                const uint32_t bal = __ballot_sync(0xffffffff, on);
+                if (lane == 0 && j >= hh * Kh && j < (hh + 1) * Kh) {
+                    cfl_half[(j - hh * Kh) >> 5] = bal == 0xffffffffu ? 0 : (bal != 0u ? 1 : 2);
+                    cbits_half[(j - hh * Kh) >> 5] = bal;
+                }
                 mine_clear &= on;
                 mine_on |= on;
             }
-            const bool clear = a3_bar_red_and(bar_id, 256, mine_clear);
-            const bool any_on = a3_bar_red_or(bar_id, 256, mine_on);
+            const bool clear = a3_bar_red_and(bar_id, 256, mine_clear);  // no masked / out-of-range key at all
+            const bool any_on = a3_bar_red_or(bar_id, 256, mine_on);    // (the barriers also publish the flags)
+            int n_eff = nloc;  // this thread's chunks up to the last one with a valid key
+            if (!clear)
+                while (n_eff > 0 && cflag[n_eff - 1] == 2) --n_eff;
             for (int t = 0; t < nqt; ++t, ++g) {
                 const uint32_t ph = g & 1;
                 const int i = t * kA3QT + r;
@@ -400,7 +434,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                         tmem_st_32x16(tS + cc * 16, pk);
                     }
                 } else {
-                    const float mine = clear ? a3_rowmax<false>(tS, nloc, pm) : a3_rowmax<true>(tS, nloc, pm);
+                    if (!clear) a3_mask_prepass(tS, n_eff, cbits, cflag);
+                    const float mine = a3_rowmax<false>(tS, n_eff, nullptr);
                     xmax[(hh * 2 + cs) * kA3QT + r] = mine;
                     a3_bar_sync(bar_id, 256);  // the row's other column thread has published its maximum
                     const float mraw = fmaxf(mine, xmax[(hh * 2 + (cs ^ 1)) * kA3QT + r]);
@@ -408,8 +443,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     // relative positions (key - query) of this warp's 32 rows x this thread's first chunk
                     const int key0 = hh * Kh + cb * 32, row0 = t * kA3QT + quarter * 32;
                     const float* pb1 = T0 + start + cb * 32;
-                    l = clear ? a3_emit<kF16, false>(tS, nloc, scale_log2e, c, pb2, pb1, pm, key0 - (row0 + 31), key0 + 31 - row0, rneg, rpos)
-                              : a3_emit<kF16, true>(tS, nloc, scale_log2e, c, pb2, pb1, pm, key0 - (row0 + 31), key0 + 31 - row0, rneg, rpos);
+                    l = a3_emit<kF16, false>(tS, n_eff, scale_log2e, c, pb2, pb1, nullptr, key0 - (row0 + 31), key0 + 31 - row0, rneg, rpos);
+                    if (!clear) a3_mask_postpass(tS, n_eff, nloc);
                 }
                 exch[((ph * 2 + hh) * 2 + cs) * kA3QT + r] = make_float2(c, l);
                 tmem_st_wait();

@@ -15,6 +15,9 @@ for (B, S) in shapes:
             bk = torch.tensor([lib.arb_mpnet_relative_bucket(int(r), 32, 128) for r in range(-511, 512)], device="cuda")
             relb = (torch.randn(32, 12, device="cuda") * 0.7)[bk].t().contiguous()
         mask = torch.ones(B, S, device="cuda", dtype=torch.int32)
+        if os.environ.get("ATTN_RAGGED"):  # lengths S - (b mod R): what a length-sorted batch of real chunks looks like
+            lens = S - (torch.arange(B, device="cuda") % int(os.environ["ATTN_RAGGED"]))
+            mask = (torch.arange(S, device="cuda")[None, :] < lens[:, None]).int().contiguous()
         ctx = torch.empty(B * S, H, device="cuda", dtype=dt)
         fl = 4.0 * B * 12 * S * S * 64
         line = f"attention B{B} S{S} {str(dt)[6:]}:"
