@@ -14,7 +14,6 @@ staging buffers and streams only. There is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Iterable, Sequence
 
 import numpy as np
 

@@ -1,6 +1,6 @@
 """Sustained small-Q search: time per pass, SM clock and power for several Q (is the HBM-bound pass power-capped,
 and do zero query rows of the 128-row MMA tile cost power?).   python tools/power_probe.py"""
-import os, subprocess, sys, threading, time
+import os, subprocess, sys, threading
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from arxiv_rag_b200.search import CorpusIndex
