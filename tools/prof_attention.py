@@ -5,7 +5,8 @@ from arxiv_rag_b200 import _lib
 lib = _lib.lib()
 B, S, H = int(os.environ.get("PROF_B", 1024)), int(os.environ.get("PROF_S", 384)), 768
 qkv = torch.randn(B * S, 3 * H, device="cuda").to(torch.bfloat16)
-relb = torch.randn(12, 1023, device="cuda")
+bk = torch.tensor([lib.arb_mpnet_relative_bucket(int(r), 32, 128) for r in range(-511, 512)], device="cuda")
+relb = (torch.randn(32, 12, device="cuda") * 0.7)[bk].t().contiguous()  # the table as MPNet builds it (32 buckets)
 mask = torch.ones(B, S, device="cuda", dtype=torch.int32)
 ctx = torch.empty(B * S, H, device="cuda", dtype=torch.bfloat16)
 for impl in [int(x) for x in os.environ.get("PROF_IMPLS", "2,3").split(",")]:
