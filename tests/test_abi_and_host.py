@@ -66,6 +66,29 @@ def test_integration_stub_binding(lib):
         ns["check"](ns["lib"].arb_mpnet_encode(0, 0, 0, 1, 1, 0, 0))
 
 
+def test_integration_stub_tokenizer(lib):
+    """INTEGRATION.md's tokenizer block, verbatim, on top of its binding block: same ids as the
+    in-tree Python tokenizer (itself checked against transformers' MPNetTokenizer)."""
+    from arxiv_rag_b200.tokenizer import WordPieceTokenizer
+
+    vocab = ["<s>", "<pad>", "</s>", "[UNK]", "<mask>"] + "the quick brown fox jump ##s ##ed over lazy dog . , cafe 你 好".split()
+    texts = ["The quick brown foxes jumped over the lazy dog.", "Café 你好, dogs", "", "zzz " * 500]
+    ns: dict = {"vocab": vocab, "texts": texts}
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        exec(compile(integration_stub("binding"), "INTEGRATION.md:stub:binding", "exec"), ns)
+        exec(compile(integration_stub("tokenizer"), "INTEGRATION.md:stub:tokenizer", "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    py = WordPieceTokenizer({t: i for i, t in enumerate(vocab)}, kind="mpnet", max_length=384)
+    assert not ns["redo"].any()
+    for row, n, text in zip(ns["input_ids"], ns["lengths"], texts):
+        want = py.encode(text)
+        assert row[:n].tolist() == want and (row[n:] == vocab.index("<pad>")).all()
+    assert ns["attention_mask"].sum(1).tolist() == ns["lengths"].tolist() and int(ns["lengths"][3]) == 384
+
+
 def test_argument_errors_return_codes_not_crashes(lib):
     assert lib.arb_topk_search_workspace_bytes(_lib.ARB_DTYPE_BF16, 0, 10, 768, 10) == 0
     assert lib.arb_topk_search_workspace_bytes(_lib.ARB_DTYPE_BF16, 128, 1_000_000, 768, 10) > 0
