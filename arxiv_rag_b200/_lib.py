@@ -88,6 +88,7 @@ SIGNATURES = {
     "arb_set_gemm_mode": (C.c_int, [_I32]),
     "arb_set_pdl_mode": (C.c_int, [_I32]),
     "arb_set_search_mode": (C.c_int, [_I32]),
+    "arb_set_search_pace": (C.c_int, [_I32]),
     "arb_gemm16_lnfold": (C.c_int, [_VP, _I64, _VP, _I64, _VP, _I64, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _I32, _I32, _VP,
                                     C.c_float, _I64, _I32, _I32, _I32, _I32, _VP]),
     "arb_topk_exchange_bytes": (_SZ, [_I32, _SZ]),

@@ -572,6 +572,11 @@ int arb_set_search_mode(int32_t mode) {
     return ARB_OK;
 }
 
+int arb_set_search_pace(int32_t on) {
+    search_pace_ref() = on != 0;
+    return ARB_OK;
+}
+
 int arb_set_pdl_mode(int32_t mode) {
     ARB_REQUIRE(mode >= 0 && mode <= 2, "pdl mode %d must be 0 (never), 1 (latency-bound calls) or 2 (always)", mode);
     pdl_mode_ref() = mode;

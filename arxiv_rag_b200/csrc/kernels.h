@@ -107,6 +107,7 @@ int launch_topk_merge(const float* scores, const int64_t* ids, int G, int64_t Q,
                       float* out_scores, int64_t* out_ids, cudaStream_t stream);
 // Search schedule override: 0 auto, 1 one CTA per 128-query tile, 2 CTA pairs per 256 queries.
 void set_search_mode(int mode);
+bool& search_pace_ref();
 // GEMM schedule override for tests/benchmarks: 0 auto, 1 one CTA per 128x256 tile, 2 CTA pairs per 256x256 tile.
 void set_gemm_mode(int mode);
 // One rank's [Q,k] result as a single buffer (fp32 scores, then 8-byte aligned int64 ids), and the

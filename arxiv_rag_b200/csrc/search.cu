@@ -40,6 +40,14 @@ constexpr int kSharedSplitMaxChunks = 1000;  // ~390 MB of bf16 rows: see make_p
 // 0 = auto (pairs as soon as there is more than one query tile), 1 = single CTA, 2 = pairs
 static int g_search_mode = 0;
 void set_search_mode(int mode) { g_search_mode = mode; }
+// pacing of the units that share a corpus split (SearchTileIter): on unless ARB_SEARCH_PACE=0; arb_set_search_pace
+bool& search_pace_ref() {
+    static bool on = []() {
+        const char* e = getenv("ARB_SEARCH_PACE");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
 
 static SearchPlan make_plan(int64_t Q, int64_t N, int k) {
     SearchPlan p;
@@ -996,11 +1004,7 @@ static int launch_search_16(const uint16_t* q, const uint16_t* corpus, int64_t Q
     int32_t* part_ids = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) + align_up(per * 4, 256));
 
     // pacing slots, one per work item (SearchTileIter); ARB_SEARCH_PACE=0 switches the pacing off (A/B)
-    static const bool pace = []() {
-        const char* e = getenv("ARB_SEARCH_PACE");
-        return !(e && e[0] == '0');
-    }();
-    int* progress = pace ? reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + 2 * align_up(per * 4, 256) +
+    int* progress = search_pace_ref() ? reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + 2 * align_up(per * 4, 256) +
                                                   align_up(static_cast<size_t>(padded_queries(Q, p.pair)) * D * 2, 256))
                          : nullptr;
     const int64_t Qp = padded_queries(Q, p.pair);

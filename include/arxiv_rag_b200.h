@@ -159,6 +159,10 @@ int arb_topk_merge(const float* scores_dev, const int64_t* ids_dev, int32_t G, i
  * pairs whenever there is more than one query tile. The workspace size depends on the mode: query it
  * after setting the mode. */
 int arb_set_search_mode(int32_t mode);
+/* Pacing of the work units that walk the same corpus split (they keep within a few chunks of each other
+ * so the split's chunks are shared through L2; process-wide, initial value 1 unless ARB_SEARCH_PACE=0).
+ * Results do not depend on it; the GPU tests compare them. */
+int arb_set_search_pace(int32_t on);
 /* Row-sharded search moves each rank's result in ONE all-gather: a record is the rank's [Q,k]
  * float32 scores followed, at arb_topk_record_ids_offset (8-byte aligned), by its [Q,k] int64 ids —
  * pass those two addresses to arb_topk_search as out_scores_dev / out_ids_dev. arb_topk_merge_records

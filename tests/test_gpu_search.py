@@ -113,6 +113,36 @@ def test_pair_schedule_equals_single_cta(cuda, bf16, shape):
     assert rep["ok"], rep
 
 
+@pytest.mark.parametrize("shape", [(4096, 120_000, 10), (700, 90_000, 10), (2100, 60_000, 100)])
+def test_split_pacing_does_not_change_results(cuda, shape):
+    """Work units that walk the same corpus split keep within a few chunks of each other through
+    progress slots in the workspace (arb_set_search_pace). That only changes WHEN a unit loads a chunk:
+    ids and scores are identical with the pacing off, in both schedules, call after call on the same
+    (uninitialised, then stale) workspace."""
+    from arxiv_rag_b200 import _lib
+
+    Q, N, k = shape
+    c = so.synthetic_unit_rows(N, 768, seed=12, bf16=True, plant_ties=True)
+    q = so.synthetic_unit_rows(Q, 768, seed=13, bf16=True)
+    lib = _lib.lib()
+    out = {}
+    try:
+        for pace in (0, 1):
+            for mode in (1, 2):
+                _lib.check(lib.arb_set_search_pace(pace))
+                _lib.check(lib.arb_set_search_mode(mode))
+                for rep in range(2):
+                    out[(pace, mode, rep)] = _run(q, c, k, True, id_offset=3)
+    finally:
+        _lib.check(lib.arb_set_search_pace(1))
+        _lib.check(lib.arb_set_search_mode(0))
+    first = out[(0, 1, 0)]
+    for key, o in out.items():
+        assert np.array_equal(o[1], first[1]) and np.array_equal(o[0], first[0]), key
+    rep = so.check_topk(first[0][:256], first[1][:256], q[:256], c, k, tol=TOL, id_offset=3)  # and they are right
+    assert rep["ok"], rep
+
+
 def test_cfg1_reference_case(cuda):
     """BASELINE configs[0] search half: 1k queries over 10k rows, top-10, fp32."""
     c = so.synthetic_unit_rows(10_000, 768, seed=0)
