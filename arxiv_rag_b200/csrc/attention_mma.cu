@@ -23,7 +23,7 @@ namespace arb {
 
 // shortest sequence the encoder sends to the tcgen05 attention in auto mode
 constexpr int kAttnTcMinSeq = 64;
-constexpr int kAttnSplitMinSeq = 256;  // auto: attention_tc3 above this length
+constexpr int kAttnSplitMinSeq = 192;  // auto: attention_tc3 above this length
 
 constexpr int kAttnThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -303,7 +303,7 @@ int launch_attention_mma(const h16* qkv, const float* rel_bias, int max_rel, con
 
 // impl: 0 = auto, 1 = mma.sync, 2 = tcgen05, 3 = tcgen05 with sub-block pipelining (experiment, only in
 // builds with -DARB_WITH_ATTENTION_TC2), 4 = tcgen05 with 16 softmax warps (attention_tc3.cu). impl 2 and 4
-// cover head dim 64, 1 <= S <= 384; auto picks 2 for 64 <= S <= 256, 4 for 256 < S <= 384, else mma.sync;
+// cover head dim 64, 1 <= S <= 384; auto picks 2 for 64 <= S <= 192, 4 for 192 < S <= 384, else mma.sync;
 // ARB_ATTN_IMPL overrides auto for A/B runs.
 int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const int32_t* mask,
                      h16* ctx, int B, int S, int heads, int dh, bool fp16, int impl, cudaStream_t stream) {
@@ -313,8 +313,9 @@ int launch_attention(const h16* qkv, const float* rel_bias, int max_rel, const i
             const char* e = getenv("ARB_ATTN_IMPL");
             return e ? atoi(e) : 0;
         }();
-        // 16 softmax warps (attention_tc3.cu) from three query tiles / 160-key halves up: 5-9 % faster than
-        // the 8-warp kernel at S = 272..384, equal at 256, slower below (fewer columns per thread than latency)
+        // 16 softmax warps (attention_tc3.cu) above S = 192: 5-9 % faster than the 8-warp kernel at
+        // S = 272..384, 1-4 % at 224..256 (4 % on ragged batches, +0.7 % on an all-valid S = 256 one),
+        // slower from 192 down (fewer columns per thread than latency to hide)
         impl = forced >= 1 && forced <= 4 ? forced : (S > kAttnSplitMinSeq ? 4 : 2);
         if (impl == 4 && !(rel_bias != nullptr && attention_tc3_supported(S, dh) && S >= kAttnTcMinSeq)) impl = 1;
         if (impl == 3 && !(rel_bias != nullptr && attention_tc2_supported(S, dh) && S >= kAttnTcMinSeq)) impl = 1;

@@ -264,7 +264,7 @@ int arb_layernorm16(const void* x, const float* gamma, const float* beta, void* 
                     int32_t H, float eps, int32_t dtype, void* stream);
 int arb_attention16(const void* qkv, const float* rel_bias, int32_t max_rel, const int32_t* mask,
                     void* ctx, int32_t B, int32_t S, int32_t heads, int32_t head_dim, int32_t dtype,
-                    int32_t impl /* 0 auto, 1 mma.sync kernel, 2 tcgen05 kernel, 8 softmax warps (head dim 64, S <= 384; auto: 64 <= S <= 256), 3 experimental (ARB_ERR_UNSUPPORTED in default builds), 4 tcgen05 kernel, 16 softmax warps (auto: 256 < S <= 384) */,
+                    int32_t impl /* 0 auto, 1 mma.sync kernel, 2 tcgen05 kernel, 8 softmax warps (head dim 64, S <= 384; auto: 64 <= S <= 192), 3 experimental (ARB_ERR_UNSUPPORTED in default builds), 4 tcgen05 kernel, 16 softmax warps (auto: 192 < S <= 384) */,
                     void* stream);
 int arb_pool_normalize(const void* hidden16, const int32_t* mask, float* out, int32_t B, int32_t S,
                        int32_t H, int32_t dtype, void* stream);
